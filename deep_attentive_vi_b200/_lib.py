@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI in ``include/davi.h`` (libdavi.so).
+
+This is the only place the shared library is loaded.  There is no fallback of
+any kind: if the library is missing or a call fails, a ``DaviError`` is raised.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdavi.so")
+
+_f = ctypes.c_void_p      # device pointer (float*)
+_i = ctypes.c_int
+_l = ctypes.c_int64
+_r = ctypes.c_float
+_s = ctypes.c_void_p      # cudaStream_t
+_z = ctypes.c_size_t
+_pp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/davi.h declaration by declaration
+SIGNATURES = {
+    "davi_version": (_i, []),
+    "davi_last_error": (_i, [ctypes.c_char_p, _z]),
+    "davi_dw_attn_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _l, _l, _f, _s]),
+    "davi_dw_attn_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _l, _l, _f, _s]),
+    "davi_dw_attn_slots_fwd": (_i, [_f, _pp, _pp, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _f, _s]),
+    "davi_dw_attn_slots_bwd": (_i, [_f, _pp, _pp, _f, _f, _pp, _pp, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _f, _i, _s]),
+    "davi_ln_gelu_fwd": (_i, [_f, _f, _f, _f, _l, _i, _l, _l, _r, _i, _s]),
+    "davi_ln_gelu_bwd_workspace_bytes": (_z, [_l, _i]),
+    "davi_ln_gelu_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _l, _i, _l, _l, _l, _r, _i, _f, _z, _s]),
+    "davi_nonlocal_attn_fwd": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _l, _l, _l, _l, _l, _f, _f, _s]),
+    "davi_nonlocal_attn_bwd_workspace_bytes": (_z, [_i, _i, _i, _i]),
+    "davi_nonlocal_attn_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _l, _l, _l, _l, _f, _f, _f, _z, _s]),
+    "davi_gauss_kl_fwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _r, _r, _r, _r, _r, _r, _s]),
+    "davi_gauss_kl_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _r, _r, _r, _r, _r, _r, _s]),
+    "davi_dlm_nll_fwd": (_i, [_f, _f, _f, _f, _i, _i, _r, _s]),
+    "davi_bernoulli_nll_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _s]),
+    "davi_scale_rows": (_i, [_f, _f, _f, _i, _l, _s]),
+    "davi_is_logsumexp": (_i, [_f, _f, _i, _i, _s]),
+}
+
+
+class DaviError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libdavi.so (building nothing: see build.py).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DaviError(
+            f"{LIB_PATH} not found: build it with `python -m deep_attentive_vi_b200.build` "
+            "(there is no CPU or PyTorch fallback for the hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    buf = ctypes.create_string_buffer(512)
+    load().davi_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise DaviError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a non-zero code."""
+    check(getattr(load(), name)(*args), name)
+
+
+def ptr_table(ptrs):
+    """Host array of device pointers for the *_slots_* entry points."""
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    return ctypes.cast(arr, _pp), arr  # keep `arr` alive for the duration of the call

@@ -1,0 +1,76 @@
+"""Build the C-ABI shared library (libdavi.so) in-tree with nvcc for sm_100a.
+
+No torch types cross the boundary, so this is a plain ``nvcc -shared`` of
+``csrc/*.cu`` against ``include/davi.h``; the result lands next to this file so
+it travels with the repo snapshot to the GPU box.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdavi.so")
+STAMP = os.path.join(HERE, "libdavi.stamp")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--expt-relaxed-constexpr", "--extended-lambda",
+    "-Xcompiler", "-fPIC",
+    "-shared",
+]
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+    h = hashlib.sha256()
+    for p in _sources() + sorted(
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
+    ) + [os.path.join(ROOT, "include", "davi.h")]:
+        with open(p, "rb") as f:
+            h.update(p.encode() + b"\0" + f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def nvcc_path():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build(force=False, verbose=False):
+    """Compile libdavi.so if sources changed.  Returns the library path."""
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+        with open(STAMP) as f:
+            if f.read().strip() == dig:
+                return LIB
+    nvcc = nvcc_path()
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; cannot build libdavi.so")
+    defines = []
+    if os.path.exists(os.path.join(CSRC, "nonlocal_tc.cu")):
+        defines.append("-DDAVI_HAVE_NONLOCAL_TC")
+    cmd = [nvcc] + NVCC_FLAGS + defines + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", LIB + ".tmp"] + _sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(LIB + ".tmp", LIB)
+    with open(STAMP, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

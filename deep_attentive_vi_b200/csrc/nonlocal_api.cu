@@ -1,0 +1,75 @@
+// C-ABI entry points of the nonlocal attention core (include/davi.h, R4) and
+// the dispatch between the tensor-core kernel (nonlocal_tc.cu) and the
+// exact-fp32 CUDA-core kernel (nonlocal_simt.cu).
+#include <stdlib.h>
+#include <string.h>
+
+#include "davi_common.cuh"
+
+namespace davi {
+int nonlocal_fwd_simt_launch(const float*, const float*, const float*, const float*, float*, float*,
+                             int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, const float*,
+                             const float*, cudaStream_t);
+int nonlocal_bwd_simt_launch(const float*, const float*, const float*, const float*, const float*,
+                             float*, float*, float*, float*, int, int, int, int, int64_t, int64_t,
+                             int64_t, int64_t, const float*, const float*, float*, cudaStream_t);
+#ifdef DAVI_HAVE_NONLOCAL_TC
+bool nonlocal_tc_supported(int B, int N, int d, int C);
+int nonlocal_fwd_tc_launch(const float*, const float*, const float*, const float*, float*, float*,
+                           int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, const float*,
+                           const float*, cudaStream_t);
+#endif
+
+// DAVI_NONLOCAL_IMPL=simt forces the exact-fp32 kernels (read once per process).
+static bool force_simt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAVI_NONLOCAL_IMPL");
+        v = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+}  // namespace davi
+
+using namespace davi;
+
+extern "C" int davi_nonlocal_attn_fwd(const float* Q, const float* K, const float* V, const float* x,
+                                      float* y, float* lse, int B, int N, int d, int C, int64_t q_s,
+                                      int64_t k_s, int64_t v_s, int64_t x_s, int64_t y_s, const float* scale,
+                                      const float* gamma, davi_stream_t stream) {
+    DAVI_REQUIRE(Q && K && V && x && y && lse && gamma, "null pointer");
+    DAVI_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(x) && aligned16(y), "alignment");
+    DAVI_REQUIRE(mult4(q_s) && mult4(k_s) && mult4(v_s) && mult4(x_s) && mult4(y_s), "strides % 4");
+    DAVI_REQUIRE(q_s >= d && k_s >= d && v_s >= C && x_s >= C && y_s >= C, "strides >= width");
+#ifdef DAVI_HAVE_NONLOCAL_TC
+    if (!force_simt() && nonlocal_tc_supported(B, N, d, C))
+        return nonlocal_fwd_tc_launch(Q, K, V, x, y, lse, B, N, d, C, q_s, k_s, v_s, x_s, y_s, scale,
+                                      gamma, (cudaStream_t)stream);
+#endif
+    (void)force_simt;
+    return nonlocal_fwd_simt_launch(Q, K, V, x, y, lse, B, N, d, C, q_s, k_s, v_s, x_s, y_s, scale, gamma,
+                                    (cudaStream_t)stream);
+}
+
+extern "C" size_t davi_nonlocal_attn_bwd_workspace_bytes(int B, int N, int d, int C) {
+    (void)d; (void)C;
+    return (size_t)B * (size_t)N * sizeof(float);
+}
+
+extern "C" int davi_nonlocal_attn_bwd(const float* Q, const float* K, const float* V, const float* lse,
+                                      const float* dy, float* dQ, float* dK, float* dV,
+                                      float* dgamma_dscale, int B, int N, int d, int C, int64_t q_s,
+                                      int64_t k_s, int64_t v_s, int64_t dy_s, const float* scale,
+                                      const float* gamma, void* workspace, size_t workspace_bytes, davi_stream_t stream) {
+    DAVI_REQUIRE(Q && K && V && lse && dy && dQ && dK && dV && dgamma_dscale && gamma, "null pointer");
+    DAVI_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(dy) && aligned16(dQ) &&
+                     aligned16(dK) && aligned16(dV), "alignment");
+    DAVI_REQUIRE(mult4(q_s) && mult4(k_s) && mult4(v_s) && mult4(dy_s), "strides % 4");
+    DAVI_REQUIRE(q_s >= d && k_s >= d && v_s >= C && dy_s >= C, "strides >= width");
+    if (!workspace || workspace_bytes < davi_nonlocal_attn_bwd_workspace_bytes(B, N, d, C)) {
+        set_error("%s: workspace too small", __func__);
+        return DAVI_EWORKSPACE;
+    }
+    return nonlocal_bwd_simt_launch(Q, K, V, lse, dy, dQ, dK, dV, dgamma_dscale, B, N, d, C, q_s, k_s, v_s,
+                                    dy_s, scale, gamma, (float*)workspace, (cudaStream_t)stream);
+}

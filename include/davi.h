@@ -1,0 +1,238 @@
+/*
+ * davi.h -- C ABI of the B200 (sm_100a) attention + ELBO hot path of the
+ * Deep Attentive VAE (reference: ifiaposto/Deep_Attentive_VI, paths below are
+ * relative to its src/ directory).
+ *
+ * The reference has no FFI: its seams are Python call signatures
+ * (DepthWiseAttention.apply, NonlocalResNetBlock.call, GaussianDiag /
+ * DiscretizedLogisticMixture / Bernoulli .log_prob, tfp kl_divergence).  Each
+ * entry point below replaces the body behind one of those seams and cites it.
+ * A TensorFlow custom-op shim (tf_ops/) or the in-tree ctypes binding
+ * (deep_attentive_vi_b200/_lib.py) binds exactly these symbols; see
+ * INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer to fp32 data, 16-byte aligned, owned by
+ *     the caller; the library never allocates, frees or retains pointers;
+ *   - tensors are channels-last (NHWC); "P" is the number of pixels H*W of one
+ *     image, flattened row-major exactly like the reference's [B,W,H,.] tensors;
+ *   - channel counts (d, C, z ...) and all strides are multiples of 4 floats
+ *     where the argument says "stride"; strides are in FLOATS;
+ *   - calls only enqueue work on `stream` (a cudaStream_t) on the calling
+ *     thread's current device and return; no host synchronisation, no default
+ *     stream use, no mutable global state (re-entrant across host threads);
+ *   - return 0 on success or a negative DAVI_E* code; never abort, never throw.
+ *     davi_last_error() returns the calling thread's last message;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns DAVI_ECUDA.
+ */
+#ifndef DAVI_H_
+#define DAVI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAVI_VERSION 100          /* major*100 + minor */
+#define DAVI_MAX_SLOTS 32         /* max stacked layers n of the depth-wise attention */
+
+#define DAVI_OK 0
+#define DAVI_EINVAL (-1)          /* bad shape / stride / alignment / null pointer */
+#define DAVI_EWORKSPACE (-2)      /* workspace too small */
+#define DAVI_ECUDA (-3)           /* CUDA runtime error (text via davi_last_error) */
+
+typedef void* davi_stream_t;      /* cudaStream_t */
+
+int davi_version(void);
+/* copies the calling thread's last error text (NUL terminated) into buf */
+int davi_last_error(char* buf, size_t buf_bytes);
+
+/* ------------------------------------------------------------------------
+ * R1  Depth-wise attention, stacked tensors.
+ * Replaces DepthWiseAttention.apply (layers/attention.py:135-164) together
+ * with SoftmaxAlignment.call (layers/attention.py:98-116):
+ *     s_j = scale * <q_p, K_{j,p}>,  a = softmax_j(s),  out_p = sum_j a_j V_{j,p}
+ * q   [B,P,d]   pixel stride q_sp
+ * K   [B,n,P,d] strides k_sb (batch), k_sn (layer), k_sp (pixel)
+ * V   [B,n,P,C] strides v_sb, v_sn, v_sp
+ * out [B,P,C]   pixel stride o_sp
+ * attn (nullable) [B,P,n] dense: the softmax weights, for inspection/tests.
+ * scale: DEVICE pointer to the learnable scalar of SoftmaxAlignment
+ * (layers/attention.py:84-92), or NULL for 1.0 -- a device scalar so that no
+ * host synchronisation is needed to read a trained value.
+ * 1 <= n <= DAVI_MAX_SLOTS.  No 1/sqrt(d) factor (the reference has none).
+ * ---------------------------------------------------------------------- */
+int davi_dw_attn_fwd(const float* q, const float* keys, const float* values,
+                     float* out, float* attn,
+                     int B, int n, int P, int d, int C,
+                     int64_t q_sp,
+                     int64_t k_sb, int64_t k_sn, int64_t k_sp,
+                     int64_t v_sb, int64_t v_sn, int64_t v_sp,
+                     int64_t o_sp,
+                     const float* scale, davi_stream_t stream);
+
+/* Hand-written gradient of the above; the softmax is
+ * recomputed from q and K.  dq/dkeys/dvalues use the SAME strides as their
+ * forward tensors.  dscale (nullable): ONE float, overwritten with
+ * sum_{pixels} sum_j ds_j * <q,K_j>. */
+int davi_dw_attn_bwd(const float* q, const float* keys, const float* values,
+                     const float* dout,
+                     float* dq, float* dkeys, float* dvalues, float* dscale,
+                     int B, int n, int P, int d, int C,
+                     int64_t q_sp,
+                     int64_t k_sb, int64_t k_sn, int64_t k_sp,
+                     int64_t v_sb, int64_t v_sn, int64_t v_sp,
+                     int64_t o_sp,
+                     const float* scale, davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * R1/R2/R3  Depth-wise attention over a LIST of context slots (no tf.stack).
+ * Replaces the stack -> split -> unstack/stack -> apply sequence of
+ * model/vae.py:339-350 + model/variational_layer.py:357-360,396-406,472-499:
+ * slot j contributes keys k_ptrs[j] [B,P,d] and values v_ptrs[j] [B,P,C], all
+ * slots sharing (k_sb,k_sp) / (v_sb,v_sp).  k_ptrs / v_ptrs are HOST arrays of
+ * n device pointers (copied into the launch arguments, not retained).
+ * ---------------------------------------------------------------------- */
+int davi_dw_attn_slots_fwd(const float* q, const float* const* k_ptrs,
+                           const float* const* v_ptrs, float* out, float* attn,
+                           int B, int n, int P, int d, int C,
+                           int64_t q_sp, int64_t k_sb, int64_t k_sp,
+                           int64_t v_sb, int64_t v_sp, int64_t o_sp,
+                           const float* scale, davi_stream_t stream);
+
+/* accumulate != 0: dk_ptrs[j] / dv_ptrs[j] are read-modify-written (+=) so one
+ * gradient buffer per context collects the contributions of every later layer
+ * (replaces TF's add_n over the L-1 consumers).  A NULL entry skips that slot. */
+int davi_dw_attn_slots_bwd(const float* q, const float* const* k_ptrs,
+                           const float* const* v_ptrs, const float* dout,
+                           float* dq, float* const* dk_ptrs, float* const* dv_ptrs,
+                           float* dscale,
+                           int B, int n, int P, int d, int C,
+                           int64_t q_sp, int64_t k_sb, int64_t k_sp,
+                           int64_t v_sb, int64_t v_sp, int64_t o_sp,
+                           const float* scale, int accumulate, davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * R2/R3 glue: LayerNormalization(epsilon) over the last axis, optionally with
+ * the "x + gelu(LN(x))" residual of model/variational_layer.py:394,409,502,503
+ * (tfa gelu, tanh form).  mode 0: y = LN(x) (vl.py:399, vae.py:347-348);
+ * mode 1: y = x + gelu(LN(x)).  x,y [rows,C] with row strides x_s,y_s.
+ * y may alias x.  gamma/beta [C].
+ * ---------------------------------------------------------------------- */
+int davi_ln_gelu_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                     int64_t rows, int C, int64_t x_s, int64_t y_s,
+                     float eps, int mode, davi_stream_t stream);
+/* dgamma/dbeta [C] are OVERWRITTEN.  workspace: davi_ln_gelu_bwd_workspace_bytes. */
+size_t davi_ln_gelu_bwd_workspace_bytes(int64_t rows, int C);
+int davi_ln_gelu_bwd(const float* x, const float* gamma, const float* beta,
+                     const float* dy, float* dx, float* dgamma, float* dbeta,
+                     int64_t rows, int C, int64_t x_s, int64_t dy_s, int64_t dx_s,
+                     float eps, int mode, void* workspace, size_t workspace_bytes,
+                     davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * R4  Nonlocal spatial self-attention core.
+ * Replaces NonlocalResNetBlock.call lines layers/attention.py:318-389 (after
+ * the three 1x1 convs, which stay host-side):
+ *     O = softmax_rows(scale * Q K^T) V,   y = gamma * O + x
+ * Q,K [B,N,d] (row strides q_s,k_s), V [B,N,C] (v_s), x,y [B,N,C] (x_s,y_s);
+ * batch strides are N*row_stride.  lse [B,N] dense: row log-sum-exp of the
+ * scaled logits, saved for the backward.  d % 4 == 0, d <= 64, C % 4 == 0.
+ * scale (nullable = 1.0) and gamma are DEVICE scalars: the trained weights
+ * `scale` (layers/attention.py:84-92) and `gamma` (layers/attention.py:256-261).
+ * ---------------------------------------------------------------------- */
+int davi_nonlocal_attn_fwd(const float* Q, const float* K, const float* V,
+                           const float* x, float* y, float* lse,
+                           int B, int N, int d, int C,
+                           int64_t q_s, int64_t k_s, int64_t v_s, int64_t x_s, int64_t y_s,
+                           const float* scale, const float* gamma, davi_stream_t stream);
+
+/* Gradient: dy [B,N,C] -> dQ,dK,dV (same strides as
+ * Q,K,V); dx == dy is left to the caller.  dgamma_dscale: TWO floats,
+ * overwritten with { sum(O*dy), sum(dS * QK^T) }.
+ * workspace: davi_nonlocal_attn_bwd_workspace_bytes. */
+size_t davi_nonlocal_attn_bwd_workspace_bytes(int B, int N, int d, int C);
+int davi_nonlocal_attn_bwd(const float* Q, const float* K, const float* V,
+                           const float* lse, const float* dy,
+                           float* dQ, float* dK, float* dV, float* dgamma_dscale,
+                           int B, int N, int d, int C,
+                           int64_t q_s, int64_t k_s, int64_t v_s, int64_t dy_s,
+                           const float* scale, const float* gamma,
+                           void* workspace, size_t workspace_bytes, davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * R5/R6  Bounded residual Gaussians: sample + KL (+ log q, log p).
+ * Replaces GaussianDiag.call/create_params/sample (stat_tools/gaussian_diag.py:
+ * 121-240), tfp kl_divergence at model/variational_layer.py:533-542 and the
+ * importance-sampling log-probs of vl.py:513-527.
+ *   post  [B,P,2z] raw (d_mu || d_logsigma) from the posterior net
+ *   prior [B,P,2z] raw (mu_p || logsigma_p) = prior.params(), or NULL for
+ *         layer 0 (p = N(0,I), posterior not residual)
+ *   eps   [B,P,z]  standard normal;  xi [B,P,z] = loc_q + sigma_q * eps
+ *   noise_post / noise_prior (nullable) [B,P,z] standard normal, scaled by
+ *         noise_std_* and added to the log-sigma halves (gd.py:165-166)
+ *   kl [B]; logq, logp (nullable) [B]
+ *   bounds: loc = 5 tanh(mu/10); sigma = exp(bound(ls, lo, hi)) + 1e-2 with
+ *         tanh form when |lo| == |hi| else smoothstep (gd.py:175-185).
+ * ---------------------------------------------------------------------- */
+int davi_gauss_kl_fwd(const float* post, const float* prior, const float* eps,
+                      const float* noise_post, const float* noise_prior,
+                      float* xi, float* kl, float* logq, float* logp,
+                      int B, int P, int z,
+                      float post_lo, float post_hi, float prior_lo, float prior_hi,
+                      float noise_std_post, float noise_std_prior,
+                      davi_stream_t stream);
+
+/* Gradient: dxi [B,P,z] (nullable = 0) and dkl [B] (nullable = 0) ->
+ * dpost [B,P,2z], dprior [B,P,2z] (NULL iff prior is NULL).  The raw prior
+ * parameters receive gradient through BOTH p and the residual q. */
+int davi_gauss_kl_bwd(const float* post, const float* prior, const float* eps,
+                      const float* noise_post, const float* noise_prior,
+                      const float* dxi, const float* dkl,
+                      float* dpost, float* dprior,
+                      int B, int P, int z,
+                      float post_lo, float post_hi, float prior_lo, float prior_hi,
+                      float noise_std_post, float noise_std_prior,
+                      davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * R7  Discretized-logistic-mixture negative log-likelihood, forward (+ fused
+ * gradient).  Replaces DiscretizedLogisticMixture.create_params/log_prob
+ * (stat_tools/discretized_logistic_mixture.py:161-211,311-412) and the negation
+ * of model/data_layer.py:179-181.  5 mixtures, 3 channels (RGB autoregression),
+ * params [B,P,50], x [B,P,3] in [-1,1]; nll [B] = -log p(x).
+ * dparams (nullable) [B,P,50] = d nll[b] / d params (per image, UNWEIGHTED);
+ * upstream weights are applied with davi_scale_rows.
+ * ---------------------------------------------------------------------- */
+int davi_dlm_nll_fwd(const float* params, const float* x, float* nll, float* dparams,
+                     int B, int P, float log_scale_low_bound, davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * R8  Bernoulli negative log-likelihood with the border crop of
+ * stat_tools/bernoulli.py:155-179: logits,x [B,H,W] (1 channel), pixels with
+ * crop <= h < H-crop and crop <= w < W-crop contribute.  nll [B];
+ * dlogits (nullable) [B,H,W] = sigmoid(l) - x inside the crop, 0 outside.
+ * ---------------------------------------------------------------------- */
+int davi_bernoulli_nll_fwd(const float* logits, const float* x, float* nll, float* dlogits,
+                           int B, int H, int W, int crop, davi_stream_t stream);
+
+/* out[b, :] = w[b] * in[b, :]  (per-image upstream weight for the fused
+ * gradients above).  in/out [B,per_image], may alias. */
+int davi_scale_rows(const float* in, const float* w, float* out,
+                    int B, int64_t per_image, davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * R10 Importance-sampled log-likelihood combine (model/vae.py:465-482,539):
+ *   l[s,b] = sum_layers(logp - logq)[s*B+b] - nll[s*B+b]   (sample-major)
+ *   out[b] = logsumexp_s l[s,b]
+ * lw [S*B] is the per-sample log-weight already summed over layers.
+ * ---------------------------------------------------------------------- */
+int davi_is_logsumexp(const float* lw, float* out, int S, int B, davi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAVI_H_ */
