@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of BASELINE.json's metric: CIFAR-10 16-layer attentive VAE train
+images/sec (batch 40 per GPU, synthetic data, random-init weights).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels via the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, restated
+                                                            # (oracle/, torch CPU, all host threads)
+
+One JSON line on stdout (rank 0).  A "step" is one full optimisation step of the
+model (forward, backward, gradient all-reduce, fused Adamax) on one batch of 40
+synthetic images per GPU.  `value` is measured with the batches already resident
+in HBM; `e2e` repeats the measurement through the public API with pinned-host
+inputs copied H2D every step and the step's loss read back D2H.
+`roofline` reports the depth-wise attention kernels (the memory-bound hot kernel
+north_star names): algorithmic bytes / CUDA-event time of the model's 31 forward
++ 31 backward calls at this batch size, each timed alone after an L2 flush.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cifar10_16layer_attentive_vae_train_images_per_sec"
+UNIT = "images/s"
+WORKLOAD = "cifar10-16layer-attentive-vae-118.97M, latent [16,16,20], key/query 20, nonlocal 32, batch 40/GPU"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 7 for n, v in zip(names, s[3:7]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the reference's CPU path restated op for op (oracle/)
+# ---------------------------------------------------------------------------
+
+def oracle_setup(batch, seed=0):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from deep_attentive_vi_b200.model import CIFAR10_16L, DeepVAE, parse_flags
+    from oracle.model import OracleVAE
+    kw = parse_flags(**CIFAR10_16L)
+    torch.manual_seed(seed)
+    m = DeepVAE(**kw)                       # CPU construction only: supplies shapes + random-init weights
+    o = OracleVAE(helpers.oracle_cfg(kw), m.state_dict(), dtype=torch.float32)
+    params = [v for k, v in o.sd.items() if v.is_floating_point() and "running" not in k]
+    for v in params:
+        v.requires_grad_()
+    x = helpers.synthetic_images(kw, batch, seed=1000)
+    return m, o, params, x
+
+
+def oracle_step(m, o, params, x, state, lr=0.01):
+    """fwd + bwd (autograd = what TF autodiff does) + Adamax, all on the host cores."""
+    import torch
+    eps, noise = m.draw_noise(x.shape[0], "cpu", training=True)
+    nll, kl, _ = o.forward(x, eps, True, noise)
+    loss = nll.mean() + kl.mean()
+    for p in params:
+        p.grad = None
+    loss.backward()
+    state["t"] += 1
+    with torch.no_grad():
+        for i, p in enumerate(params):
+            if p.grad is None:
+                continue
+            mom, u = state["m"].setdefault(i, torch.zeros_like(p)), state["u"].setdefault(i, torch.zeros_like(p))
+            mom.mul_(0.9).add_(p.grad, alpha=0.1)
+            torch.maximum(u.mul_(0.999), p.grad.abs(), out=u)
+            p.addcdiv_(mom, u + 1e-3, value=-lr / (1 - 0.9 ** state["t"]))
+    return float(loss)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = args.ref_batch
+    m, o, params, x = oracle_setup(batch)
+    state = {"t": 0, "m": {}, "u": {}}
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle_step(m, o, params, x, state)
+    t0 = time.time()
+    for _ in range(args.steps):
+        oracle_step(m, o, params, x, state)
+    dt = (time.time() - t0) / args.steps
+    val = batch / dt
+    sample = f"{args.steps} full train steps (fwd+bwd+Adamax) of the same model at batch {batch} (fp32, torch CPU)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "bounded CPU sample: batch %d per step" % batch},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# roofline of the depth-wise attention kernels (the model's 62 calls per step)
+# ---------------------------------------------------------------------------
+
+def dw_roofline(batch, device):
+    import torch
+    from deep_attentive_vi_b200 import _lib
+    L, d, HW, P = 16, 20, 16, 256
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
+    calls = [("dec", i, 276) for i in range(1, L)] + [("enc", L + 1 - i, 256) for i in range(L)]
+    nmax = L + 1
+    Cmax = 276
+    K = torch.randn(batch, nmax, HW, HW, d, device=device)
+    V = torch.randn(batch, nmax, HW, HW, Cmax, device=device)
+    q = torch.randn(batch, HW, HW, d, device=device)
+    go = torch.randn(batch, HW, HW, Cmax, device=device)
+    out = torch.empty(batch, HW, HW, Cmax, device=device)
+    dK, dV, dq = torch.empty_like(K), torch.empty_like(V), torch.empty_like(q)
+    tot_b = tot_t = 0.0
+    per_call = []
+    for kind, n, C in calls:
+        k, v = K[:, :n].contiguous(), V[:, :n, ..., :C].contiguous()
+        dk, dv = dK[:, :n].contiguous(), dV[:, :n, ..., :C].contiguous()
+        o_, g_ = out[..., :C].contiguous(), go[..., :C].contiguous()
+        fb = 4 * batch * P * (n * (d + C) + d + C)
+        bb = 4 * batch * P * (2 * n * (d + C) + 2 * d + C)
+        fa = (q.data_ptr(), k.data_ptr(), v.data_ptr(), o_.data_ptr(), 0, batch, n, P, d, C,
+              d, n * P * d, P * d, d, n * P * C, P * C, C, C, 0, stream)
+        ba = (q.data_ptr(), k.data_ptr(), v.data_ptr(), g_.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+              dv.data_ptr(), 0, batch, n, P, d, C, d, n * P * d, P * d, d, n * P * C, P * C, C, C, 0, stream)
+        for name, a, nbytes in (("davi_dw_attn_fwd", fa, fb), ("davi_dw_attn_bwd", ba, bb)):
+            ts = []
+            for rep in range(4):
+                flush.fill_(0.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.call(name, *a)
+                e1.record()
+                e1.synchronize()
+                if rep:
+                    ts.append(e0.elapsed_time(e1))
+            t = sorted(ts)[len(ts) // 2]
+            tot_b += nbytes
+            tot_t += t
+            per_call.append({"k": name[-3:], "n": n, "C": C, "us": round(t * 1e3, 1),
+                             "GBs": round(nbytes / t / 1e6)})
+    return tot_b, tot_t, per_call
+
+
+# ---------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------
+
+def run_davi(args):
+    import torch
+    import torch.distributed as dist
+    from deep_attentive_vi_b200 import _lib, build
+    from deep_attentive_vi_b200.model import CIFAR10_16L, DeepVAE, parse_flags
+    from deep_attentive_vi_b200.util.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    _lib.load()
+    # hot-path kernels compute in fp32; the host-side cuDNN convolutions use TF32 tensor cores
+    torch.backends.cudnn.allow_tf32 = not args.fp32_convs
+    torch.backends.cuda.matmul.allow_tf32 = not args.fp32_convs
+    torch.backends.cudnn.benchmark = True
+
+    B = args.batch
+    torch.manual_seed(0)
+    model = DeepVAE(**parse_flags(**CIFAR10_16L)).to(device)
+    trainer = Trainer(model, device=device, world_size=world, rank=rank)
+    nparams = model.count_params()
+
+    g = torch.Generator().manual_seed(1000 + rank)
+    nbuf = 4
+    host = [torch.randint(0, 256, (B, 32, 32, 3), generator=g).float().pin_memory() for _ in range(nbuf)]
+    dev_in = [h.to(device) for h in host]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def timed(loop_body, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            loop_body(s)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident_step(s):
+        trainer.train_step(dev_in[s % nbuf])
+
+    last = {}
+
+    def e2e_step(s):
+        x = host[s % nbuf].to(device, non_blocking=True)          # H2D from pinned memory
+        nll, kl = trainer.train_step(x)
+        last["loss"] = float((nll.mean() + kl.mean()).item())      # D2H read of the step's loss
+
+    for s in range(args.warmup):
+        resident_step(s)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    calls0 = _lib.launch_count()
+    ms = timed(resident_step, args.steps)
+    launches = _lib.launch_count() - calls0
+    for s in range(min(args.warmup, 2)):
+        e2e_step(s)
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    value = B * world * args.steps / (ms / 1e3)
+    e2e_val = B * world * args.steps / (ms_e2e / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "params": nparams,
+                   "parallelism": f"dp{world}", "convs": "cuDNN fp32" if args.fp32_convs else "cuDNN tf32",
+                   "l2": "inputs (2 GB activations per step) exceed L2; dw-attention roofline calls are "
+                         "timed after an explicit 256 MB L2 flush"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 32 * 3 * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss")},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if not args.no_roofline:
+            peak, which = measured_peak()
+            tb, tt, per_call = dw_roofline(B, device)
+            ach = tb / tt / 1e6
+            line["roofline"] = {"bound": "hbm", "kernel": "dw_attn_fwd/bwd (62 calls of one step)",
+                                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": which, "traffic": None,
+                                "algorithmic_MB_per_step": tb / 1e6, "kernel_ms_per_step": tt,
+                                "per_call": per_call}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cb = args.ref_batch
+            m, o, params, x = oracle_setup(cb)
+            state = {"t": 0, "m": {}, "u": {}}
+            oracle_step(m, o, params, x, state)
+            t0 = time.time()
+            n = 2
+            for _ in range(n):
+                oracle_step(m, o, params, x, state)
+            dt = (time.time() - t0) / n
+            line["cpu_baseline"] = {"value": cb / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} full train steps of the same model at batch {cb} "
+                                              "(oracle/, torch CPU fp32, all host threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="davi", choices=["davi", "reference"])
+    ap.add_argument("--batch", type=int, default=40, help="images per GPU (BASELINE config: 40)")
+    ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
+    ap.add_argument("--fp32-convs", action="store_true", help="disable TF32 in the host-side cuDNN convs")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_davi(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -37,6 +37,7 @@ SIGNATURES = {
     "davi_bernoulli_nll_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _s]),
     "davi_scale_rows": (_i, [_f, _f, _f, _i, _l, _s]),
     "davi_is_logsumexp": (_i, [_f, _f, _i, _i, _s]),
+    "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
 }
 
 
@@ -76,9 +77,21 @@ def check(rc, what):
         raise DaviError(f"{what} failed (rc={rc}): {last_error()}")
 
 
+# kernels launched by one successful call of each entry point (bench.py's
+# `gpu_launches` claim is the sum over the timed region)
+KERNELS_PER_CALL = {"davi_ln_gelu_bwd": 2, "davi_nonlocal_attn_bwd": 2}
+_launches = 0
+
+
+def launch_count():
+    return _launches
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero code."""
+    global _launches
     check(getattr(load(), name)(*args), name)
+    _launches += KERNELS_PER_CALL.get(name, 1)
 
 
 def ptr_table(ptrs):

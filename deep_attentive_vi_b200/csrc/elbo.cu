@@ -233,12 +233,16 @@ dlm_nll_kernel(const float* __restrict__ params, const float* __restrict__ x,
                     dm = -inv * w; dl = -mn * w;
                 } else {
                     const float cp = sigmoidf(plus), cm = sigmoidf(mn);
-                    const float delta = cp - cm;
+                    // sigma(plus) - sigma(mn) without cancellation:
+                    //   = sigma(plus) * sigma(-mn) * (1 - exp(mn - plus))
+                    const float delta = cp * sigmoidf(-mn) * (-expm1f(mn - plus));
                     if (delta > 1e-5f) {
                         lp = logf(fmaxf(delta, 1e-12f));
-                        const float gp = cp * (1.f - cp), gm = cm * (1.f - cm);
-                        dm = -inv * (gp - gm) / delta;
-                        dl = (-plus * gp + mn * gm) / delta;
+                        // (gp - gm) / delta == 1 - cp - cm exactly (g = c (1 - c))
+                        const float gsum = cp * (1.f - cp) + cm * (1.f - cm);
+                        const float hw = inv * (1.f / 255.f), mid = inv * u;
+                        dm = -inv * (1.f - cp - cm);
+                        dl = -mid * (1.f - cp - cm) - hw * gsum / delta;
                     } else {
                         const float mid = inv * u;
                         lp = mid - ls - 2.f * softplusf(mid) - 4.848116405963898f;   // log(127.5)

@@ -1,0 +1,76 @@
+"""Weight-normalised convolution: host-side restatement of the reference's
+WeightNorm(tf.keras.layers.Conv2D) (layers/weight_norm.py:126-143,225-239).
+
+kernel = l2_normalize(v, over all axes but the output filter) * exp(log_g);
+log_g is initialised to log||v|| + 1e-2 on the first call (_init_norm).
+Tensors are NHWC; the convolution itself is cuDNN through torch on a
+channels_last view (dense convs are outside the hot-path scope).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .util import deep_vae_init_
+
+
+def to_nchw(x):  # [B,H,W,C] contiguous -> NCHW view in channels_last memory format (no copy)
+    return x.permute(0, 3, 1, 2)
+
+
+def to_nhwc(y):  # inverse; copies only if cuDNN returned a non-channels_last tensor
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+class WNConv2d(nn.Module):
+    def __init__(self, cin, cout, kernel_size=1, strides=1, use_bias=True, padding="same",
+                 use_weight_norm=True, lambda_reg=1.5e-4):
+        super().__init__()
+        k = kernel_size
+        self.k, self.strides, self.padding, self.use_weight_norm = k, strides, padding, use_weight_norm
+        v = torch.empty(cout, cin, k, k)
+        deep_vae_init_(v, fan_in=k * k * cin)                                   # res.py:596
+        self.v = nn.Parameter(v.contiguous(memory_format=torch.channels_last))
+        if use_weight_norm:
+            norm = self.v.detach().flatten(1).norm(dim=1)
+            self.log_g = nn.Parameter(torch.log(norm) + 1e-2)                    # weight_norm.py:139-143
+        if use_bias:
+            self.bias = nn.Parameter(deep_vae_init_(torch.empty(cout), fan_in=cout))  # res.py:597
+        else:
+            self.bias = None
+        self.lambda_reg = lambda_reg
+
+    def kernel(self):
+        if not self.use_weight_norm:
+            return self.v
+        # tf.nn.l2_normalize: v * rsqrt(max(sum v^2, 1e-12))                     weight_norm.py:133-134
+        ss = self.v.square().sum(dim=(1, 2, 3), keepdim=True).clamp_min(1e-12)
+        return self.v * (torch.exp(self.log_g).view(-1, 1, 1, 1) * torch.rsqrt(ss))
+
+    def forward(self, x):
+        """x [B,H,W,Cin] -> [B,H',W',Cout]."""
+        xc = to_nchw(x)
+        k, s = self.k, self.strides
+        if self.padding == "same":
+            H, W = x.shape[1], x.shape[2]
+            # TF 'same': total = max((ceil(n/s)-1)*s + k - n, 0); before = total//2, rest after
+            def pads(n):
+                out = -(-n // s)
+                tot = max((out - 1) * s + k - n, 0)
+                return tot // 2, tot - tot // 2
+            (pt, pb), (pl, pr) = pads(H), pads(W)
+            if pt == pb and pl == pr:
+                y = F.conv2d(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl))
+            else:
+                y = F.conv2d(F.pad(xc, (pl, pr, pt, pb)), self.kernel(), self.bias, stride=s)
+        else:
+            y = F.conv2d(xc, self.kernel(), self.bias, stride=s)
+        return to_nhwc(y)
+
+    def reg_loss(self):
+        """l2(lambda_reg) on v, g and bias (res.py:564-566, weight_norm.py:213)."""
+        r = self.v.square().sum()
+        if self.use_weight_norm:
+            r = r + self.log_g.square().sum()
+        if self.bias is not None:
+            r = r + self.bias.square().sum()
+        return self.lambda_reg * r

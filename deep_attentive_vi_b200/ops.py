@@ -277,6 +277,15 @@ def nonlocal_attn(q, k, v, x, scale, gamma):
     """y = gamma * softmax(scale * q k^T) v + x over the H*W positions of each
     image (reference layers/attention.py:318-389).  q,k [B,H,W,d]; v,x [B,H,W,C]
     (channel-slice views allowed); scale (or None), gamma: 0-dim tensors."""
+    C = x.shape[-1]
+    if C % 4:
+        # rows must be 16-byte multiples for the vector loads (the 138-channel
+        # pre-processing blocks of the CIFAR-10 model): zero-pad the channel axis,
+        # the pad columns of V contribute zeros and are sliced away again.
+        pad = 4 - C % 4
+        v = torch.nn.functional.pad(v, (0, pad))
+        xp = torch.nn.functional.pad(x, (0, pad))
+        return _NonlocalAttn.apply(q, k, v, xp, scale, gamma)[..., :C]
     return _NonlocalAttn.apply(q, k, v, x, scale, gamma)
 
 

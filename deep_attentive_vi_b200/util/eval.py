@@ -1,0 +1,56 @@
+"""Importance-sampled test log-likelihood, sharded by SAMPLE across ranks --
+replaces the reference's util/eval.py:140-146 + model/vae.py:485-539 (there:
+data-parallel over images with a serial while_loop over sample chunks).
+
+Rank r draws K/world of the K importance samples for the SAME image batch,
+reduces them with a local logsumexp and the ranks' partial results are combined
+with one tiny all-gather: logsumexp is associative, exactly like the reference's
+own nesting of two logsumexps over chunks (vae.py:482,539)."""
+import math
+
+import torch
+import torch.distributed as dist
+
+from ..util.hparams import HParams
+
+
+def get_default_eval_hparams():
+    """ev.py:189-201."""
+    return HParams(num_gpus=2, generate=True, reconstruct=True, compute_logp=True,
+                   num_importance_samples=100, num_sample_images=32, num_test_images=32, workers=25,
+                   batch_size=16, shuffle=True, verbose=True)
+
+
+def shard_samples(num_samples, world, rank):
+    """Samples [lo, hi) owned by `rank` (remainder to the last rank, as the
+    reference gives the remainder to the last chunk, vae.py:524)."""
+    per = num_samples // world
+    lo = rank * per
+    hi = num_samples if rank == world - 1 else lo + per
+    return lo, hi
+
+
+def combine_partial_logsumexp(partials, num_samples):
+    """partials [world, B] -> log p_hat(x) [B] (vae.py:539)."""
+    return torch.logsumexp(partials, dim=0) - math.log(num_samples)
+
+
+@torch.no_grad()
+def importance_log_likelihood(model, x, num_samples, max_chunk=25, world=1, rank=0, group=None):
+    """log p_hat(x) [B] with K = num_samples importance samples, this rank
+    computing its shard in chunks of at most `max_chunk` samples."""
+    lo, hi = shard_samples(num_samples, world, rank)
+    parts = []
+    k = lo
+    while k < hi:
+        n = min(max_chunk, hi - k)
+        parts.append(model.infer_worker_body(x, n))
+        k += n
+    local = torch.logsumexp(torch.stack(parts, 0), dim=0)            # [B]
+    if world > 1:
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local, group=group)
+        partials = torch.stack(gathered, 0)
+    else:
+        partials = local.unsqueeze(0)
+    return combine_partial_logsumexp(partials, num_samples)

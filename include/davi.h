@@ -232,6 +232,17 @@ int davi_scale_rows(const float* in, const float* w, float* out,
  * ---------------------------------------------------------------------- */
 int davi_is_logsumexp(const float* lw, float* out, int S, int B, davi_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * 8(f4)  Fused Adamax step over flat arrays (replaces tf.keras.optimizers.Adamax
+ * of util/trainer.py:156-157,226-231 with the Keras l2 regulariser gradient
+ * 2*l2*w of layers/resnet.py:564-566 folded in):
+ *   g' = grad_scale*g + 2*l2*p;  m = b1 m + (1-b1) g';  u = max(b2 u, |g'|);
+ *   p -= lr / (1 - b1^step) * m / (u + eps).        step counts from 1.
+ * ---------------------------------------------------------------------- */
+int davi_adamax_step(float* param, const float* grad, float* m, float* u, int64_t n,
+                     float lr, float beta1, float beta2, float eps, int64_t step,
+                     float l2, float grad_scale, davi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
