@@ -113,7 +113,7 @@ def oracle_step(m, o, params, x, state, lr=0.01):
             mom.mul_(0.9).add_(p.grad, alpha=0.1)
             torch.maximum(u.mul_(0.999), p.grad.abs(), out=u)
             p.addcdiv_(mom, u + 1e-3, value=-lr / (1 - 0.9 ** state["t"]))
-    return float(loss)
+    return float(loss.detach())
 
 
 def run_reference(args):
@@ -299,8 +299,10 @@ def run_davi(args):
             line["roofline"] = {"bound": "hbm", "kernel": "dw_attn_fwd/bwd (62 calls of one step)",
                                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": which, "traffic": None,
-                                "algorithmic_MB_per_step": tb / 1e6, "kernel_ms_per_step": tt,
-                                "per_call": per_call}
+                                "algorithmic_MB_per_step": tb / 1e6, "kernel_ms_per_step": tt}
+            if args.roofline_detail:
+                with open(args.roofline_detail, "w") as f:
+                    json.dump(per_call, f)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
@@ -332,6 +334,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--fp32-convs", action="store_true", help="disable TF32 in the host-side cuDNN convs")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--roofline-detail", default="", help="write the per-call dw-attention timings here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

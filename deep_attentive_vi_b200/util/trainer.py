@@ -72,8 +72,8 @@ class FlatState:
         for n, p in named:
             groups.setdefault(l2_coefficient(n), []).append((n, p))
         total = sum(p.numel() for _, p in named)
-        pad = lambda k: (k + 3) // 4 * 4
-        size = sum(pad(sum(p.numel() for _, p in g)) for g in groups.values())
+        pad = lambda k: (k + 63) // 64 * 64   # every tensor starts 256-byte aligned (cuDNN, float4 loads)
+        size = sum(sum(pad(p.numel()) for _, p in g) for g in groups.values())
         self.P = torch.zeros(size, device=device)
         self.G = torch.zeros(size, device=device)
         self.M = torch.zeros(size, device=device)
@@ -95,9 +95,8 @@ class FlatState:
                     self.P[off:off + n].view(p.shape).copy_(src)
                     p.data = self.P[off:off + n].view(p.shape)
                     p.grad = self.G[off:off + n].view(p.shape)
-                off += n
+                off += pad(n)
             self.segments.append((float(l2), start, off - start))
-            off = pad(off)
         assert off == size
 
 
