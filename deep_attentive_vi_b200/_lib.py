@@ -38,6 +38,7 @@ SIGNATURES = {
     "davi_scale_rows": (_i, [_f, _f, _f, _i, _l, _s]),
     "davi_is_logsumexp": (_i, [_f, _f, _i, _i, _s]),
     "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
+    "davi_adamax_step_dev": (_i, [_f, _f, _f, _f, _l, _f, _r, _r, _r, _r, _s]),
 }
 
 
@@ -85,6 +86,12 @@ _launches = 0
 
 def launch_count():
     return _launches
+
+
+def add_launches(n):
+    """Account for kernels launched without a Python-level call (CUDA-graph replays)."""
+    global _launches
+    _launches += n
 
 
 def call(name, *args):

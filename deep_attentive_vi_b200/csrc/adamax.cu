@@ -10,7 +10,11 @@ namespace davi {
 __global__ void __launch_bounds__(256)
 adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
               float* __restrict__ u, int64_t n4, int64_t n, float lr_t, float b1, float b2,
-              float eps, float l2x2, float gscale) {
+              float eps, float l2x2, float gscale, const float* __restrict__ hyper) {
+    if (hyper) {   // device-resident step size: a captured CUDA graph replays with fresh values
+        lr_t = __ldg(hyper);
+        gscale = __ldg(hyper + 1);
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pv = reinterpret_cast<float4*>(p)[i];
@@ -54,6 +58,21 @@ extern "C" int davi_adamax_step(float* param, const float* grad, float* m, float
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     adamax_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, u, n4, n, lr_t, beta1,
-                                                                 beta2, eps, 2.f * l2, grad_scale);
+                                                                 beta2, eps, 2.f * l2, grad_scale, nullptr);
+    return check_launch(__func__);
+}
+
+extern "C" int davi_adamax_step_dev(float* param, const float* grad, float* m, float* u, int64_t n,
+                                    const float* hyper, float beta1, float beta2, float eps, float l2,
+                                    davi_stream_t stream) {
+    using namespace davi;
+    DAVI_REQUIRE(param && grad && m && u && hyper && n > 0, "arguments");
+    DAVI_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(u), "alignment");
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    adamax_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, u, n4, n, 0.f, beta1, beta2,
+                                                                 eps, 2.f * l2, 1.f, hyper);
     return check_launch(__func__);
 }

@@ -101,7 +101,14 @@ class FlatState:
 
 
 class Trainer:
-    def __init__(self, model, hparams=None, device="cuda", world_size=1, rank=0, steps_per_epoch=1250):
+    """use_graph=True captures the whole optimisation step (forward, hand-written
+    backward kernels, NCCL all-reduce, fused Adamax) into ONE CUDA graph after
+    `graph_warmup` eager steps and replays it afterwards: the ~10^4 launches of a
+    step then cost one host call.  Everything that changes between steps lives in
+    device memory (input batch, KL weight beta, Adamax step size)."""
+
+    def __init__(self, model, hparams=None, device="cuda", world_size=1, rank=0, steps_per_epoch=1250,
+                 use_graph=False, graph_warmup=3):
         self.model = model
         self.hp = hparams or get_default_train_hparams()
         self.device = torch.device(device)
@@ -113,16 +120,27 @@ class Trainer:
         self.lr = self.hp.learning_rate
         for b in model.buffers():
             assert b.device.type == "cuda", "move the model to the GPU before building the Trainer"
+        # device-resident step state (read by the kernels, so a captured graph sees fresh values)
+        self.beta_dev = torch.ones((), device=self.device)
+        self.hyper_dev = torch.tensor([0.0, 1.0], device=self.device)   # [lr / (1 - b1^t), grad_scale]
+        self.lr_dev = torch.full((1,), float(self.lr), device=self.device)
+        self.step_dev = torch.zeros(1, device=self.device)              # t, advanced on the device
+        self._lr_pushed = float(self.lr)
+        self.use_graph, self.graph_warmup = use_graph, graph_warmup
+        self._graph = None
+        self._static = None
+        self.graph_launches = 0
 
     def set_epoch(self, epoch):
         self.beta = kl_beta(epoch, self.hp.kl_warmup_epochs, self.hp.kl_warmup_smooth_start)
+        self.beta_dev.fill_(self.beta)
 
     def forward_backward(self, x, eps=None, noise=None):
         st = self.state
         st.G.zero_()
         nll, kl, nelbo = self.model(x, True, eps, noise)
         global_batch = x.shape[0] * self.world                       # tr.py:174
-        loss = (nll.sum() + self.beta * kl.sum()) * (1.0 / global_batch)
+        loss = (nll.sum() + self.beta_dev * kl.sum()) * (1.0 / global_batch)
         loss.backward()
         return nll, kl
 
@@ -132,20 +150,56 @@ class Trainer:
         if self.world > 1:
             dist.all_reduce(self.state.G, op=dist.ReduceOp.SUM)
 
+    def _advance_hyper(self):
+        """Host side of the optimizer step: count it, push a changed learning rate
+        (fill_ carries the value in the launch arguments: no pinned-buffer race)."""
+        self.step_count += 1
+        if float(self.lr) != self._lr_pushed:
+            self._lr_pushed = float(self.lr)
+            self.lr_dev.fill_(self._lr_pushed)
+
     def apply(self):
         st, hp = self.state, self.hp
-        self.step_count += 1
+        # Keras Adamax bias correction lr / (1 - beta_1^t), t kept on the device
+        self.step_dev.add_(1.0)
+        corr = 1.0 - torch.pow(torch.full_like(self.step_dev, float(hp.keras_lr_beta_1)), self.step_dev)
+        self.hyper_dev[0:1].copy_(self.lr_dev / corr)
         stream = torch.cuda.current_stream().cuda_stream
         for l2, off, n in st.segments:
-            _lib.call("davi_adamax_step", st.P[off:].data_ptr(), st.G[off:].data_ptr(),
-                      st.M[off:].data_ptr(), st.U[off:].data_ptr(), n, float(self.lr),
+            _lib.call("davi_adamax_step_dev", st.P[off:].data_ptr(), st.G[off:].data_ptr(),
+                      st.M[off:].data_ptr(), st.U[off:].data_ptr(), n, self.hyper_dev.data_ptr(),
                       float(hp.keras_lr_beta_1), float(hp.keras_lr_beta_2), float(hp.keras_lr_epsilon),
-                      self.step_count, l2, 1.0, stream)
+                      l2, stream)
 
-    def train_step(self, x, eps=None, noise=None):
-        """One optimisation step on this rank's shard x [B,H,W,C].  Returns the
-        per-image nll and kl tensors of the shard (device, no host sync)."""
+    def _step_body(self, x, eps=None, noise=None):
         nll, kl = self.forward_backward(x, eps, noise)
         self.all_reduce()
         self.apply()
         return nll, kl
+
+    def _capture(self, x):
+        self._static = {"x": torch.empty_like(x)}
+        self._static["x"].copy_(x)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(g):
+            nll, kl = self._step_body(self._static["x"])
+        self.graph_launches = _lib.launch_count() - before
+        _lib.add_launches(-self.graph_launches)       # capture enqueued nothing; replays are counted below
+        self._static["nll"], self._static["kl"] = nll, kl
+        self._graph = g
+
+    def train_step(self, x, eps=None, noise=None):
+        """One optimisation step on this rank's shard x [B,H,W,C].  Returns the
+        per-image nll and kl tensors of the shard (device, no host sync)."""
+        self._advance_hyper()
+        graph_ok = self.use_graph and eps is None and noise is None
+        if not graph_ok or self.step_count <= self.graph_warmup:
+            return self._step_body(x, eps, noise)
+        if self._graph is None:
+            self._capture(x)
+        self._static["x"].copy_(x, non_blocking=True)
+        self._graph.replay()
+        _lib.add_launches(self.graph_launches)
+        return self._static["nll"], self._static["kl"]

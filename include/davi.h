@@ -243,6 +243,14 @@ int davi_adamax_step(float* param, const float* grad, float* m, float* u, int64_
                      float lr, float beta1, float beta2, float eps, int64_t step,
                      float l2, float grad_scale, davi_stream_t stream);
 
+/* Same update with the step size read from DEVICE memory, so that a captured
+ * CUDA graph of the whole training step can be replayed while the learning-rate
+ * schedule and the bias correction advance: hyper[0] = lr / (1 - beta1^step),
+ * hyper[1] = grad_scale (two floats, written by the host before each replay). */
+int davi_adamax_step_dev(float* param, const float* grad, float* m, float* u, int64_t n,
+                         const float* hyper, float beta1, float beta2, float eps, float l2,
+                         davi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

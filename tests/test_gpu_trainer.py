@@ -1,0 +1,72 @@
+"""GPU tests of the training step: fused Adamax against the Keras update rule
+(reference util/trainer.py:226-231), and the CUDA-graph replay of the whole step
+against the eager step on identical inputs and noise."""
+import pytest
+import torch
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def test_adamax_matches_keras_rule(cuda):
+    from deep_attentive_vi_b200 import _lib
+    torch.manual_seed(0)
+    n = 1003                                     # ragged tail (n % 4 != 0)
+    p = torch.randn(n, device=cuda)
+    m = torch.zeros(n + 1, device=cuda)[:n]
+    u = torch.zeros(n + 1, device=cuda)[:n]
+    pr, mr, ur = p.double().cpu(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    lr, b1, b2, eps, l2 = 0.01, 0.9, 0.999, 1e-3, 1.5e-4
+    hyper = torch.zeros(2, device=cuda)
+    stream = torch.cuda.current_stream().cuda_stream
+    for t in range(1, 5):
+        g = torch.randn(n, device=cuda)
+        if t % 2:                                # host-scalar entry point
+            _lib.call("davi_adamax_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), u.data_ptr(), n,
+                      lr, b1, b2, eps, t, l2, 1.0, stream)
+        else:                                    # device-scalar entry point (CUDA-graph safe)
+            hyper.copy_(torch.tensor([lr / (1 - b1 ** t), 1.0]))
+            _lib.call("davi_adamax_step_dev", p.data_ptr(), g.data_ptr(), m.data_ptr(), u.data_ptr(), n,
+                      hyper.data_ptr(), b1, b2, eps, l2, stream)
+        gg = g.double().cpu() + 2 * l2 * pr      # Keras l2 regulariser gradient
+        mr = b1 * mr + (1 - b1) * gg
+        ur = torch.maximum(b2 * ur, gg.abs())
+        pr = pr - lr / (1 - b1 ** t) * mr / (ur + eps)
+    assert (p.double().cpu() - pr).abs().max() < 1e-5
+
+
+def test_graph_replay_equals_eager_step(cuda):
+    """Same weights, images and (fixed) noise: 3 eager warm-up steps + 3 graph
+    replays must equal 6 eager steps."""
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    from deep_attentive_vi_b200.util.trainer import Trainer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    kw = parse_flags(**helpers.SMALL_CIFAR)
+    B = 4
+    xs = [helpers.synthetic_images(kw, B, seed=s).to(cuda) for s in range(6)]
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        m = DeepVAE(**kw)
+        helpers.randomize_zero_init_scalars(m)
+        eps, noise = m.draw_noise(B, "cpu", generator=torch.Generator().manual_seed(1), training=True)
+        eps = [e.to(cuda) for e in eps]
+        noise = [None if nz is None else tuple(None if t is None else t.to(cuda) for t in nz) for nz in noise]
+        m = m.to(cuda)
+        m.draw_noise = lambda *a, **k: (eps, noise)      # fixed noise for both runs
+        tr = Trainer(m, device=cuda, use_graph=use_graph, graph_warmup=3)
+        losses = []
+        for x in xs:
+            nll, kl = tr.train_step(x)
+            losses.append((nll.mean() + kl.mean()).item())
+        assert (tr._graph is not None) == use_graph
+        results.append((losses, tr.state.P.clone(), tr.step_dev.item()))
+    (l0, p0, s0), (l1, p1, s1) = results
+    assert s0 == s1 == 6.0
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-4 * abs(a), (l0, l1)
+    assert (p0 - p1).abs().max().item() < 1e-4

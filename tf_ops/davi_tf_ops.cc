@@ -1,0 +1,341 @@
+// TensorFlow custom-op shim over the davi C ABI (include/davi.h).
+//
+// STATUS: source only.  TensorFlow (headers and runtime) is absent from the
+// build container and from the GPU boxes, so this file is NOT compiled or run
+// by the test-suite; every line of arithmetic lives behind the C ABI and is
+// exercised through the ctypes binding (deep_attentive_vi_b200/_lib.py).  Where
+// TensorFlow exists, build it with
+//
+//   TF_CFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_compile_flags()))')
+//   TF_LFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_link_flags()))')
+//   g++ -std=c++17 -shared -fPIC tf_ops/davi_tf_ops.cc -o tf_ops/libdavi_tf.so \
+//       -Iinclude $TF_CFLAGS $TF_LFLAGS -DGOOGLE_CUDA=1 \
+//       -Ldeep_attentive_vi_b200 -ldavi -Wl,-rpath,'$ORIGIN/../deep_attentive_vi_b200'
+//
+// and load it with tf.load_op_library (tf_ops/davi_tf.py registers the
+// gradients and subclasses the reference layers).
+//
+// Each op forwards raw device pointers + the op's CUDA stream to ONE C-ABI
+// entry point; outputs and workspaces are allocated by TensorFlow
+// (allocate_output / allocate_temp), errors become errors::Internal with the
+// text of davi_last_error().  There is no CPU kernel registration: placing one
+// of these ops on a CPU device fails at graph construction.
+#define EIGEN_USE_GPU
+#include "tensorflow/core/framework/op.h"
+#include "tensorflow/core/framework/op_kernel.h"
+#include "tensorflow/core/framework/shape_inference.h"
+#include "tensorflow/core/util/gpu_kernel_helper.h"
+
+#include "davi.h"
+
+namespace tf = tensorflow;
+using tf::OpKernel;
+using tf::OpKernelConstruction;
+using tf::OpKernelContext;
+using tf::Tensor;
+using tf::TensorShape;
+
+namespace {
+
+davi_stream_t StreamOf(OpKernelContext* ctx) {
+  return reinterpret_cast<davi_stream_t>(ctx->eigen_gpu_device().stream());
+}
+
+tf::Status Check(int rc, const char* what) {
+  if (rc == DAVI_OK) return tf::Status::OK();
+  char buf[512];
+  davi_last_error(buf, sizeof(buf));
+  return tf::errors::Internal(what, " failed (", rc, "): ", buf);
+}
+
+const float* P(const Tensor& t) { return t.flat<float>().data(); }
+float* P(Tensor* t) { return t->flat<float>().data(); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// DaviDwAttn: DepthWiseAttention.apply (src/layers/attention.py:135-164)
+//   query [B,W,H,d], keys [B,n,W,H,d], values [B,n,W,H,C], scale [] -> [B,W,H,C]
+// ---------------------------------------------------------------------------
+REGISTER_OP("DaviDwAttn")
+    .Input("query: float")
+    .Input("keys: float")
+    .Input("values: float")
+    .Input("scale: float")
+    .Output("out: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      tf::shape_inference::ShapeHandle v, out;
+      TF_RETURN_IF_ERROR(c->WithRank(c->input(2), 5, &v));
+      out = c->MakeShape({c->Dim(v, 0), c->Dim(v, 2), c->Dim(v, 3), c->Dim(v, 4)});
+      c->set_output(0, out);
+      return tf::Status::OK();
+    });
+
+class DaviDwAttnOp : public OpKernel {
+ public:
+  explicit DaviDwAttnOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &q = ctx->input(0), &k = ctx->input(1), &v = ctx->input(2), &s = ctx->input(3);
+    OP_REQUIRES(ctx, k.dims() == 5 && v.dims() == 5 && q.dims() == 4,
+                tf::errors::InvalidArgument("DaviDwAttn: expected ranks 4/5/5"));
+    const int B = k.dim_size(0), n = k.dim_size(1), W = k.dim_size(2), H = k.dim_size(3);
+    const int d = k.dim_size(4), C = v.dim_size(4), Pn = W * H;
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B, W, H, C}), &out));
+    OP_REQUIRES_OK(ctx, Check(davi_dw_attn_fwd(P(q), P(k), P(v), P(out), nullptr, B, n, Pn, d, C,
+                                               d, (int64_t)n * Pn * d, (int64_t)Pn * d, d,
+                                               (int64_t)n * Pn * C, (int64_t)Pn * C, C, C, P(s),
+                                               StreamOf(ctx)),
+                              "davi_dw_attn_fwd"));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("DaviDwAttn").Device(tf::DEVICE_GPU), DaviDwAttnOp);
+
+REGISTER_OP("DaviDwAttnGrad")
+    .Input("query: float")
+    .Input("keys: float")
+    .Input("values: float")
+    .Input("scale: float")
+    .Input("dout: float")
+    .Output("dquery: float")
+    .Output("dkeys: float")
+    .Output("dvalues: float")
+    .Output("dscale: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      for (int i = 0; i < 4; ++i) c->set_output(i, c->input(i));
+      return tf::Status::OK();
+    });
+
+class DaviDwAttnGradOp : public OpKernel {
+ public:
+  explicit DaviDwAttnGradOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &q = ctx->input(0), &k = ctx->input(1), &v = ctx->input(2), &s = ctx->input(3);
+    const Tensor& go = ctx->input(4);
+    const int B = k.dim_size(0), n = k.dim_size(1), W = k.dim_size(2), H = k.dim_size(3);
+    const int d = k.dim_size(4), C = v.dim_size(4), Pn = W * H;
+    Tensor *dq, *dk, *dv, *ds;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, q.shape(), &dq));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, k.shape(), &dk));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, v.shape(), &dv));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({}), &ds));
+    OP_REQUIRES_OK(ctx, Check(davi_dw_attn_bwd(P(q), P(k), P(v), P(go), P(dq), P(dk), P(dv), P(ds),
+                                               B, n, Pn, d, C, d, (int64_t)n * Pn * d,
+                                               (int64_t)Pn * d, d, (int64_t)n * Pn * C,
+                                               (int64_t)Pn * C, C, C, P(s), StreamOf(ctx)),
+                              "davi_dw_attn_bwd"));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("DaviDwAttnGrad").Device(tf::DEVICE_GPU), DaviDwAttnGradOp);
+
+// ---------------------------------------------------------------------------
+// DaviNonlocalAttn: core of NonlocalResNetBlock.call (attention.py:318-389)
+//   q,k [B,W,H,d]; v,x [B,W,H,C]; scale, gamma [] -> y [B,W,H,C], lse [B,W*H]
+// ---------------------------------------------------------------------------
+REGISTER_OP("DaviNonlocalAttn")
+    .Input("q: float").Input("k: float").Input("v: float").Input("x: float")
+    .Input("scale: float").Input("gamma: float")
+    .Output("y: float").Output("lse: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->input(3));
+      c->set_output(1, c->UnknownShapeOfRank(2));
+      return tf::Status::OK();
+    });
+
+class DaviNonlocalAttnOp : public OpKernel {
+ public:
+  explicit DaviNonlocalAttnOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &q = ctx->input(0), &k = ctx->input(1), &v = ctx->input(2), &x = ctx->input(3);
+    const int B = x.dim_size(0), N = x.dim_size(1) * x.dim_size(2);
+    const int d = q.dim_size(3), C = x.dim_size(3);
+    Tensor *y, *lse;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x.shape(), &y));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({B, N}), &lse));
+    OP_REQUIRES_OK(ctx, Check(davi_nonlocal_attn_fwd(P(q), P(k), P(v), P(x), P(y), P(lse), B, N, d, C,
+                                                     d, d, C, C, C, P(ctx->input(4)), P(ctx->input(5)),
+                                                     StreamOf(ctx)),
+                              "davi_nonlocal_attn_fwd"));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("DaviNonlocalAttn").Device(tf::DEVICE_GPU), DaviNonlocalAttnOp);
+
+REGISTER_OP("DaviNonlocalAttnGrad")
+    .Input("q: float").Input("k: float").Input("v: float").Input("lse: float")
+    .Input("scale: float").Input("gamma: float").Input("dy: float")
+    .Output("dq: float").Output("dk: float").Output("dv: float").Output("dgamma_dscale: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      for (int i = 0; i < 3; ++i) c->set_output(i, c->input(i));
+      c->set_output(3, c->Vector(2));
+      return tf::Status::OK();
+    });
+
+class DaviNonlocalAttnGradOp : public OpKernel {
+ public:
+  explicit DaviNonlocalAttnGradOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &q = ctx->input(0), &k = ctx->input(1), &v = ctx->input(2), &lse = ctx->input(3);
+    const Tensor& dy = ctx->input(6);
+    const int B = v.dim_size(0), N = v.dim_size(1) * v.dim_size(2);
+    const int d = q.dim_size(3), C = v.dim_size(3);
+    Tensor *dq, *dk, *dv, *dgs, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, q.shape(), &dq));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, k.shape(), &dk));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, v.shape(), &dv));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({2}), &dgs));
+    const size_t wsb = davi_nonlocal_attn_bwd_workspace_bytes(B, N, d, C);
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, TensorShape({(tf::int64)((wsb + 3) / 4)}), &ws));
+    OP_REQUIRES_OK(ctx, Check(davi_nonlocal_attn_bwd(P(q), P(k), P(v), P(lse), P(dy), P(dq), P(dk), P(dv),
+                                                     P(dgs), B, N, d, C, d, d, C, C, P(ctx->input(4)),
+                                                     P(ctx->input(5)), P(&ws), wsb, StreamOf(ctx)),
+                              "davi_nonlocal_attn_bwd"));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("DaviNonlocalAttnGrad").Device(tf::DEVICE_GPU), DaviNonlocalAttnGradOp);
+
+// ---------------------------------------------------------------------------
+// DaviGaussKl: GaussianDiag residual posterior sample + KL
+//   (stat_tools/gaussian_diag.py:121-240, model/variational_layer.py:511-542)
+// ---------------------------------------------------------------------------
+REGISTER_OP("DaviGaussKl")
+    .Input("post: float").Input("prior: float").Input("eps: float")
+    .Attr("post_lo: float").Attr("post_hi: float").Attr("prior_lo: float").Attr("prior_hi: float")
+    .Attr("has_prior: bool = true")
+    .Output("xi: float").Output("kl: float").Output("logq: float").Output("logp: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->input(2));
+      for (int i = 1; i < 4; ++i) c->set_output(i, c->Vector(c->Dim(c->input(2), 0)));
+      return tf::Status::OK();
+    });
+
+class DaviGaussKlOp : public OpKernel {
+ public:
+  explicit DaviGaussKlOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("post_lo", &qlo_));
+    OP_REQUIRES_OK(c, c->GetAttr("post_hi", &qhi_));
+    OP_REQUIRES_OK(c, c->GetAttr("prior_lo", &plo_));
+    OP_REQUIRES_OK(c, c->GetAttr("prior_hi", &phi_));
+    OP_REQUIRES_OK(c, c->GetAttr("has_prior", &has_prior_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &post = ctx->input(0), &prior = ctx->input(1), &eps = ctx->input(2);
+    const int B = eps.dim_size(0), Pn = eps.dim_size(1) * eps.dim_size(2), z = eps.dim_size(3);
+    Tensor *xi, *kl, *lq, *lp;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, eps.shape(), &xi));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({B}), &kl));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, TensorShape({B}), &lq));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({B}), &lp));
+    OP_REQUIRES_OK(ctx, Check(davi_gauss_kl_fwd(P(post), has_prior_ ? P(prior) : nullptr, P(eps), nullptr,
+                                                nullptr, P(xi), P(kl), P(lq), P(lp), B, Pn, z, qlo_, qhi_,
+                                                plo_, phi_, 0.f, 0.f, StreamOf(ctx)),
+                              "davi_gauss_kl_fwd"));
+  }
+ private:
+  float qlo_, qhi_, plo_, phi_;
+  bool has_prior_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviGaussKl").Device(tf::DEVICE_GPU), DaviGaussKlOp);
+
+REGISTER_OP("DaviGaussKlGrad")
+    .Input("post: float").Input("prior: float").Input("eps: float")
+    .Input("dxi: float").Input("dkl: float")
+    .Attr("post_lo: float").Attr("post_hi: float").Attr("prior_lo: float").Attr("prior_hi: float")
+    .Attr("has_prior: bool = true")
+    .Output("dpost: float").Output("dprior: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->input(0));
+      c->set_output(1, c->input(1));
+      return tf::Status::OK();
+    });
+
+class DaviGaussKlGradOp : public OpKernel {
+ public:
+  explicit DaviGaussKlGradOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("post_lo", &qlo_));
+    OP_REQUIRES_OK(c, c->GetAttr("post_hi", &qhi_));
+    OP_REQUIRES_OK(c, c->GetAttr("prior_lo", &plo_));
+    OP_REQUIRES_OK(c, c->GetAttr("prior_hi", &phi_));
+    OP_REQUIRES_OK(c, c->GetAttr("has_prior", &has_prior_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &post = ctx->input(0), &prior = ctx->input(1), &eps = ctx->input(2);
+    const int B = eps.dim_size(0), Pn = eps.dim_size(1) * eps.dim_size(2), z = eps.dim_size(3);
+    Tensor *dpost, *dprior;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, post.shape(), &dpost));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, prior.shape(), &dprior));
+    OP_REQUIRES_OK(ctx, Check(davi_gauss_kl_bwd(P(post), has_prior_ ? P(prior) : nullptr, P(eps), nullptr,
+                                                nullptr, P(ctx->input(3)), P(ctx->input(4)), P(dpost),
+                                                has_prior_ ? P(dprior) : nullptr, B, Pn, z, qlo_, qhi_,
+                                                plo_, phi_, 0.f, 0.f, StreamOf(ctx)),
+                              "davi_gauss_kl_bwd"));
+  }
+ private:
+  float qlo_, qhi_, plo_, phi_;
+  bool has_prior_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviGaussKlGrad").Device(tf::DEVICE_GPU), DaviGaussKlGradOp);
+
+// ---------------------------------------------------------------------------
+// DaviDlmNll / DaviBernoulliNll: data negative log-likelihood with the
+// per-image gradient emitted by the same launch
+//   (stat_tools/discretized_logistic_mixture.py:161-211,311-412;
+//    stat_tools/bernoulli.py:155-179; model/data_layer.py:179-181)
+// ---------------------------------------------------------------------------
+REGISTER_OP("DaviDlmNll")
+    .Input("params: float").Input("x: float")
+    .Attr("log_scale_low_bound: float = -7.0")
+    .Output("nll: float").Output("dparams: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->Vector(c->Dim(c->input(0), 0)));
+      c->set_output(1, c->input(0));
+      return tf::Status::OK();
+    });
+
+class DaviDlmNllOp : public OpKernel {
+ public:
+  explicit DaviDlmNllOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("log_scale_low_bound", &lo_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &p = ctx->input(0), &x = ctx->input(1);
+    const int B = p.dim_size(0), Pn = p.dim_size(1) * p.dim_size(2);
+    Tensor *nll, *dp;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B}), &nll));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, p.shape(), &dp));
+    OP_REQUIRES_OK(ctx, Check(davi_dlm_nll_fwd(P(p), P(x), P(nll), P(dp), B, Pn, lo_, StreamOf(ctx)),
+                              "davi_dlm_nll_fwd"));
+  }
+ private:
+  float lo_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviDlmNll").Device(tf::DEVICE_GPU), DaviDlmNllOp);
+
+REGISTER_OP("DaviBernoulliNll")
+    .Input("logits: float").Input("x: float")
+    .Attr("crop: int = 0")
+    .Output("nll: float").Output("dlogits: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->Vector(c->Dim(c->input(0), 0)));
+      c->set_output(1, c->input(0));
+      return tf::Status::OK();
+    });
+
+class DaviBernoulliNllOp : public OpKernel {
+ public:
+  explicit DaviBernoulliNllOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("crop", &crop_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &l = ctx->input(0), &x = ctx->input(1);
+    const int B = l.dim_size(0), H = l.dim_size(1), W = l.dim_size(2);
+    Tensor *nll, *dl;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B}), &nll));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, l.shape(), &dl));
+    OP_REQUIRES_OK(ctx, Check(davi_bernoulli_nll_fwd(P(l), P(x), P(nll), P(dl), B, H, W, crop_,
+                                                     StreamOf(ctx)),
+                              "davi_bernoulli_nll_fwd"));
+  }
+ private:
+  int crop_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviBernoulliNll").Device(tf::DEVICE_GPU), DaviBernoulliNllOp);
