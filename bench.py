@@ -227,7 +227,8 @@ def run_davi(args):
     B = args.batch
     torch.manual_seed(0)
     model = DeepVAE(**parse_flags(**CIFAR10_16L)).to(device)
-    trainer = Trainer(model, device=device, world_size=world, rank=rank)
+    trainer = Trainer(model, device=device, world_size=world, rank=rank, use_graph=not args.eager,
+                      graph_warmup=min(3, max(1, args.warmup - 1)))
     nparams = model.count_params()
 
     g = torch.Generator().manual_seed(1000 + rank)
@@ -283,7 +284,7 @@ def run_davi(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "params": nparams,
-                   "parallelism": f"dp{world}", "convs": "cuDNN fp32" if args.fp32_convs else "cuDNN tf32",
+                   "parallelism": f"dp{world}", "cuda_graph": not args.eager, "convs": "cuDNN fp32" if args.fp32_convs else "cuDNN tf32",
                    "l2": "inputs (2 GB activations per step) exceed L2; dw-attention roofline calls are "
                          "timed after an explicit 256 MB L2 flush"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 32 * 3 * 4,
@@ -333,6 +334,7 @@ def main():
     ap.add_argument("--batch", type=int, default=40, help="images per GPU (BASELINE config: 40)")
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--fp32-convs", action="store_true", help="disable TF32 in the host-side cuDNN convs")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-detail", default="", help="write the per-call dw-attention timings here")
     ap.add_argument("--no-cpu-baseline", action="store_true")

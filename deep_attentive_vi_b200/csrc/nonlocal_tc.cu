@@ -1,25 +1,29 @@
 // R4 (tensor-core path): nonlocal spatial self-attention core on the 5th-gen
-// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands by TMA).
 // Replaces NonlocalResNetBlock.call lines layers/attention.py:318-389:
 //     O = softmax_rows(scale * Q K^T) V ;  y = gamma * O + x
+// and, with the roles of Q and K swapped, the dV = P^T dO term of its gradient.
 //
-// The reference computes in full fp32 (TF 2.3 has no TF32), so every product is
-// error-compensated: each fp32 operand is split into tf32 (hi, lo) halves and
-// hi*hi' + lo*hi' + hi*lo' is accumulated in fp32 ("3xTF32", ~2^-21 relative per
-// product).  The [B,N,N] score matrix never exists in HBM or shared memory.
+// Precision: the reference computes in full fp32 (TF 2.3 has no TF32), so every
+// product is error-compensated ("3xTF32"): v = hi + lo with hi = the fp32 bit
+// pattern itself (the tensor core truncates it to tf32) and lo = rna_tf32(v - hi);
+// hi*hi' + lo*hi' + hi*lo' recovers the fp32 product to ~2^-21.
 //
-// One CTA owns 128 query rows of one image.  Warp roles (288 threads):
-//   warps 0-3  softmax: thread r owns query row r = TMEM lane r; row statistics,
-//              P = softmax tile -> (hi, lo) -> shared memory; final epilogue
-//   warps 4-7  loaders: global fp32 -> (hi, lo) -> UMMA canonical smem layouts
-//   warp  8    one elected thread issues every tcgen05.mma / tcgen05.commit
-// Two passes over the keys in blocks of 128 (S block = 128 TMEM columns):
-//   pass A: S = Q K_blk^T, running row max / sum (softmax statistics only)
-//   pass B: S recomputed (K-dim d <= 32: ~10 % of the PV flops), P normalised with
-//           the final statistics, O += P V in 16-key chunks through a ring of
-//           shared-memory stages; O lives in TMEM columns [128, 128 + Cp).
-// The recompute keeps TMEM within 512 columns (128 + 320) for every N, so N = 256
-// and N = 1024 run the same code and O never needs rescaling.
+// One CTA owns 128 rows (queries in the forward, keys for dV) of one image:
+//   warps 0-3   softmax: thread r <-> row r <-> TMEM lane r; P chunks go back into TMEM
+//               (tcgen05.st) and feed the P*V MMAs as TMEM-resident A operands
+//   warps 4-5   lo pass of the row tile X and the column blocks Y (K-major, SWIZZLE_128B)
+//   warps 6-7   lo pass of the value chunks W (MN-major, SWIZZLE_128B_BASE32B)
+//   warp  8     TMA producer of X / Y       warp 9   TMA producer of W
+//   warp 10     one thread issues every tcgen05.mma / tcgen05.commit
+// The [B,N,N] matrix exists only as 128x128 fp32 blocks in TMEM.  Forward = two
+// passes over the column blocks (row max first; then exp, row sum and P*V with
+// unnormalised P, divided by the row sum in the epilogue), so the accumulator is
+// never rescaled.  TMEM columns: S [0,128) | O [128,128+Cp) | P ring [448,512).
+// Instruction cost measured by tools/umma_probe2.cu (profiles/r01_umma_probe2.txt):
+// ~173 cycles per SS MMA, ~115 per TS MMA, independent of N <= 160.
+#include <cuda.h>
+
 #include "davi_common.cuh"
 #include "tc_common.cuh"
 
@@ -27,402 +31,754 @@ namespace davi {
 
 using namespace tc;
 
-constexpr int kTcM = 128;          // query rows per CTA
-constexpr int kTcKB = 128;         // keys per S block
-constexpr int kTcKC = 16;          // keys per PV chunk
-constexpr int kTcChunks = kTcKB / kTcKC;
-constexpr int kTcThreads = 288;
-constexpr int kTcMaxStages = 4;
-constexpr int kTcTmemCols = 512;
-constexpr int kTcOCol = kTcKB;     // first TMEM column of O
+constexpr int kPvM = 128;                   // rows per CTA
+constexpr int kPvKB = 128;                  // columns per S block
+constexpr int kPvKC = 16;                   // columns per P chunk
+constexpr int kPvChunks = kPvKB / kPvKC;
+constexpr int kPvThreads = 352;
+constexpr int kPvMaxStages = 4;
+constexpr int kPvOCol = 128;                // first TMEM column of the accumulator
+constexpr int kPvPCol = 448;                // P ring: 2 slots x (hi 16 | lo 16) columns
+constexpr int kTileBytes = kPvM * 32 * 4;   // one K-major [128 x 32] fp32 tile
+constexpr int kPvFixedBytes = 6 * kTileBytes;   // X raw/lo + 2 x (Y raw/lo)
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
-struct TcGeom {
-    int N, d, C, Cp;               // Cp = C rounded up to 16 (MMA N granularity)
-    int n1, n2;                    // PV instruction widths (n1 + n2 = Cp, n2 may be 0)
-    int stages;
-    int64_t q_s, k_s, v_s, x_s, y_s;
+struct PvGeom {
+    int N, d, C, Cp;        // Cp = C rounded up to 32 (TMA zero-fills the pad)
+    int nkb;                // N / 128
+    int n1, n2;             // MMA N split of Cp (n2 may be 0)
+    int stages, ksteps;     // W ring depth; ceil(d / 8)
 };
 
-struct TcBars {
-    uint64_t k_full, k_empty, s_full, s_empty, o_full;
-    uint64_t pv_full[kTcMaxStages], pv_empty[kTcMaxStages];
+struct PvArgs {
+    // MODE 0 (forward): y = gamma * O + x, lse, optional copy of O for the backward
+    const float* x; float* y; float* o_save; float* lse;
+    int64_t x_s, y_s, o_s;
+    // MODE 1 (dV): out = gamma * P^T dy, lse of the forward as input
+    const float* lse_in; float* out; int64_t out_s;
+    const float* scale; const float* gamma;
+};
+
+struct PvBars {
+    uint64_t x_full, x_ready;
+    uint64_t y_full[2], y_ready[2], y_empty[2];
+    uint64_t s_full, s_empty, o_full;
+    uint64_t w_full[kPvMaxStages], w_ready[kPvMaxStages], w_empty[kPvMaxStages];
+    uint64_t p_full[2], p_empty[2];
     uint32_t tmem_base;
 };
 
-// rows [row0, row0+128) x d of a K-major operand: global fp32 -> hi/lo tiles
-__device__ __forceinline__ void load_kmajor_tile(const float* __restrict__ src, int64_t stride, int d4,
-                                                 float* hi, float* lo, int lt) {
-    // lane -> (row%8, chunk%4): 8 rows x 64 contiguous bytes per warp instruction,
-    // and each quarter-warp stores 128 contiguous bytes (no bank conflicts)
-    const int lane = lt & 31, w = lt >> 5;
-    const int r8 = lane & 7, c4 = lane >> 3;
-    const int citems = (d4 + 3) >> 2;
-    const int items = (kTcM / 8) * citems;
-    for (int it = w; it < items; it += 4) {
-        const int rg = it / citems, cg = it - rg * citems;
-        const int r = rg * 8 + r8, kc = cg * 4 + c4;
-        if (kc < d4) {
-            const float4 v = ld4(src + (int64_t)r * stride + 4 * kc);
-            float4 h, l;
-            split4(v, h, l);
-            const int off = (kc * kTcM + r) * 4;
-            *reinterpret_cast<float4*>(hi + off) = h;
-            *reinterpret_cast<float4*>(lo + off) = l;
-        }
-    }
+// elementwise lo pass over a tile that TMA wrote (same swizzled offsets in both buffers)
+__device__ __forceinline__ void lo_pass(const uint8_t* raw, uint8_t* lo, int n_float4, int lt, int nthreads) {
+    const float4* src = reinterpret_cast<const float4*>(raw);
+    float4* dst = reinterpret_cast<float4*>(lo);
+    for (int i = lt; i < n_float4; i += nthreads) dst[i] = lo4_tf32(src[i]);
 }
 
-// 16 keys x Cp channels of V as the B operand [N = channels, K = keys] of O += P V.
-// The tensor core wants B K-major (4 consecutive KEYS per 16 bytes; MN-major tf32 is
-// not available without swizzling), V rows are channel-contiguous: each group of 4
-// lanes loads a 4-key x 4-channel block (float4 per key), transposes it with three
-// shuffles, and stores one float4 per channel:
-//     byte(c, j) = (j/4)*(Cp*16) + c*16 + (j%4)*4        (LBO = Cp*16, SBO = 128)
-// A warp item is 4 keys x 32 channels: 4 rows x 128 contiguous bytes from global,
-// 512 contiguous bytes to shared memory (no bank conflicts).
-__device__ __forceinline__ float4 transpose4(const float4& v, int jj, int lane) {
-    // round r: read from lane (jj + r) % 4 of my 4-lane group the component that
-    // lane selects for me: provider p serves receiver (p - r) % 4 with component (p - r) % 4
-    float out[4];
-    const float in[4] = {v.x, v.y, v.z, v.w};
-    const int base = lane & ~3;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int e = (jj - r) & 3;                       // component I provide this round
-        const float give = e == 0 ? in[0] : e == 1 ? in[1] : e == 2 ? in[2] : in[3];
-        const float got = r == 0 ? give : __shfl_sync(0xffffffffu, give, base + ((jj + r) & 3));
-        const int k = (jj + r) & 3;                        // key index of what I received
-        if (k == 0) out[0] = got; else if (k == 1) out[1] = got; else if (k == 2) out[2] = got; else out[3] = got;
-    }
-    return make_float4(out[0], out[1], out[2], out[3]);
-}
-
-__device__ __forceinline__ void load_v_chunk(const float* __restrict__ src, int64_t stride, int C4, int Cp,
-                                             float* hi, float* lo, int lt) {
-    const int lane = lt & 31, w = lt >> 5;
-    const int jj = lane & 3, c8 = lane >> 2;
-    const int cblocks = (Cp + 31) >> 5;
-    const int items = (kTcKC / 4) * cblocks;
-    constexpr int kBatch = 5;
-    for (int it0 = w; it0 < items; it0 += 4 * kBatch) {
-        float4 v[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int it = it0 + 4 * u;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (it < items) {
-                const int j4 = it / cblocks, cb = it - j4 * cblocks;
-                const int c4 = cb * 8 + c8;
-                if (c4 < C4) v[u] = ld_stream4(src + (int64_t)(j4 * 4 + jj) * stride + 4 * c4);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int it = it0 + 4 * u;
-            if (it < items) {                               // warp-uniform
-                const int j4 = it / cblocks, cb = it - j4 * cblocks;
-                const float4 t = transpose4(v[u], jj, lane);   // channel cb*32 + lane, keys j4*4 .. +3
-                const int c = cb * 32 + lane;
-                if (c < Cp) {
-                    float4 h, l;
-                    split4(t, h, l);
-                    const int off = (j4 * Cp + c) * 4;
-                    *reinterpret_cast<float4*>(hi + off) = h;
-                    *reinterpret_cast<float4*>(lo + off) = l;
-                }
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1)
-nonlocal_fwd_tc(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                const float* __restrict__ x, float* __restrict__ y, float* __restrict__ lse,
-                const float* __restrict__ scale_p, const float* __restrict__ gamma_p, const TcGeom g) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ TcBars bars;
+template <int MODE>
+__global__ void __launch_bounds__(kPvThreads, 1)
+nl_pv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmW, const PvArgs a, const PvGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ PvBars bars;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y, i0 = blockIdx.x * kTcM;
-    const int d4 = g.d >> 2, C4 = g.C >> 2;
-    const int nkb = g.N / kTcKB;
+    const int b = blockIdx.y, r0 = blockIdx.x * kPvM;
+    const int nchunks = g.nkb * kPvChunks;
+    const int nuse = (MODE == 0 ? 2 : 1) * g.nkb;          // S blocks issued (pass A + pass B)
 
-    // ---- shared memory carve-up ---------------------------------------------
-    const int qk_bytes = kTcM * g.d * 4;                 // one hi or lo tile of Q / K block
-    float* sQh = reinterpret_cast<float*>(smem_raw);
-    float* sQl = reinterpret_cast<float*>(smem_raw + qk_bytes);
-    float* sKh = reinterpret_cast<float*>(smem_raw + 2 * qk_bytes);
-    float* sKl = reinterpret_cast<float*>(smem_raw + 3 * qk_bytes);
-    const int p_bytes = kTcM * kTcKC * 4;                // 8 KB
-    const int v_bytes = kTcKC * g.Cp * 4;
-    const int stage_bytes = 2 * p_bytes + 2 * v_bytes;
-    uint8_t* stage0 = smem_raw + 4 * qk_bytes;
-    auto sPh = [&](int s) { return reinterpret_cast<float*>(stage0 + s * stage_bytes); };
-    auto sPl = [&](int s) { return reinterpret_cast<float*>(stage0 + s * stage_bytes + p_bytes); };
-    auto sVh = [&](int s) { return reinterpret_cast<float*>(stage0 + s * stage_bytes + 2 * p_bytes); };
-    auto sVl = [&](int s) { return reinterpret_cast<float*>(stage0 + s * stage_bytes + 2 * p_bytes + v_bytes); };
+    uint8_t* sXr = smem;
+    uint8_t* sXl = smem + kTileBytes;
+    auto sYr = [&](int i) { return smem + (2 + i) * kTileBytes; };
+    auto sYl = [&](int i) { return smem + (4 + i) * kTileBytes; };
+    const int w_bytes = kPvKC * g.Cp * 4;
+    const int blk_bytes = kPvKC * 128;                      // one 32-channel block of a W chunk
+    auto sWr = [&](int s) { return smem + kPvFixedBytes + s * 2 * w_bytes; };
+    auto sWl = [&](int s) { return smem + kPvFixedBytes + s * 2 * w_bytes + w_bytes; };
+    float* sStats = reinterpret_cast<float*>(smem + kPvFixedBytes + g.stages * 2 * w_bytes);
 
-    // ---- one-time setup -------------------------------------------------------
     if (tid == 0) {
-        mbar_init(&bars.k_full, 128);
-        mbar_init(&bars.k_empty, 1);
+        mbar_init(&bars.x_full, 1);
+        mbar_init(&bars.x_ready, 64);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.y_full[i], 1);
+            mbar_init(&bars.y_ready[i], 64);
+            mbar_init(&bars.y_empty[i], 1);
+            mbar_init(&bars.p_full[i], 128);
+            mbar_init(&bars.p_empty[i], 1);
+        }
         mbar_init(&bars.s_full, 1);
         mbar_init(&bars.s_empty, 128);
         mbar_init(&bars.o_full, 1);
-        for (int s = 0; s < kTcMaxStages; ++s) {
-            mbar_init(&bars.pv_full[s], 256);
-            mbar_init(&bars.pv_empty[s], 1);
+        for (int s = 0; s < kPvMaxStages; ++s) {
+            mbar_init(&bars.w_full[s], 1);
+            mbar_init(&bars.w_ready[s], 64);
+            mbar_init(&bars.w_empty[s], 1);
         }
         mbar_init_fence();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(&tmW);
     }
-    if (warp == 8) tmem_alloc(&bars.tmem_base, kTcTmemCols);
+    if (warp == 10) tmem_alloc(&bars.tmem_base, 512);
+    if (MODE == 1)
+        for (int i = tid; i < g.N; i += kPvThreads) sStats[i] = a.lse_in[(int64_t)b * g.N + i] * kLog2e;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars.tmem_base;
 
-    const float* Qb = Q + ((int64_t)b * g.N + i0) * g.q_s;
-    const float* Kb = K + (int64_t)b * g.N * g.k_s;
-    const float* Vb = V + (int64_t)b * g.N * g.v_s;
-
     if (warp < 4) {
         // =====================================================================
-        // softmax warps: thread r <-> query row i0 + r <-> TMEM lane r
+        // softmax warps: thread r <-> row r0 + r <-> TMEM lane r
         // =====================================================================
         const int r = tid;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        const float scale = (scale_p ? __ldg(scale_p) : 1.f) * 1.4426950408889634f;   // logits in log2 units
+        const float sc = (a.scale ? __ldg(a.scale) : 1.f) * kLog2e;     // logits in log2 units
         float m = -INFINITY, l = 0.f;
-        uint32_t n_s = 0;                       // S blocks consumed so far
-        float t[kTcKB];
+        uint32_t n_s = 0;
+        float t[kPvKB];
 
-        // ---- pass A: statistics ----
-        for (int kb = 0; kb < nkb; ++kb) {
+        auto load_s = [&]() {
             mbar_wait(&bars.s_full, n_s & 1);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < kTcKB / 32; ++c) tmem_ld32(trow + c * 32, t + c * 32);
+            for (int c = 0; c < kPvKB / 32; ++c) tmem_ld32(trow + c * 32, t + c * 32);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars.s_empty);
             ++n_s;
-            float bm = -INFINITY;
+        };
+
+        if (MODE == 0) {                                   // pass A: row max of the scaled logits
+            for (int kb = 0; kb < g.nkb; ++kb) {
+                load_s();
 #pragma unroll
-            for (int j = 0; j < kTcKB; ++j) { t[j] *= scale; bm = fmaxf(bm, t[j]); }
-            const float mn = fmaxf(m, bm);
-            float bs = 0.f;
-#pragma unroll
-            for (int j = 0; j < kTcKB; ++j) bs += exp2f(t[j] - mn);
-            l = l * exp2f(m - mn) + bs;
-            m = mn;
+                for (int j = 0; j < kPvKB; ++j) m = fmaxf(m, t[j] * sc);
+            }
         }
-        const float inv_l = 1.f / l;
-        lse[(int64_t)b * g.N + i0 + r] = (m + log2f(l)) * 0.6931471805599453f;
-
-        // ---- pass B: P tiles ----
-        uint32_t gchunk = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&bars.s_full, n_s & 1);
-            tc_fence_after();
+        uint32_t gc = 0;
+        for (int kb = 0; kb < g.nkb; ++kb) {               // pass B: P chunks -> TMEM
+            load_s();
 #pragma unroll
-            for (int c = 0; c < kTcKB / 32; ++c) tmem_ld32(trow + c * 32, t + c * 32);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bars.s_empty);
-            ++n_s;
+            for (int c = 0; c < kPvChunks; ++c, ++gc) {
+                float hi[kPvKC], lo[kPvKC];
 #pragma unroll
-            for (int c = 0; c < kTcChunks; ++c, ++gchunk) {
-                const int s = gchunk % g.stages;
-                const uint32_t use = gchunk / g.stages;
-                float4 ph[kTcKC / 4], pl[kTcKC / 4];
-#pragma unroll
-                for (int q4 = 0; q4 < kTcKC / 4; ++q4) {
-                    float4 p;
-                    p.x = exp2f(t[c * kTcKC + 4 * q4 + 0] * scale - m) * inv_l;
-                    p.y = exp2f(t[c * kTcKC + 4 * q4 + 1] * scale - m) * inv_l;
-                    p.z = exp2f(t[c * kTcKC + 4 * q4 + 2] * scale - m) * inv_l;
-                    p.w = exp2f(t[c * kTcKC + 4 * q4 + 3] * scale - m) * inv_l;
-                    split4(p, ph[q4], pl[q4]);
+                for (int j = 0; j < kPvKC; ++j) {
+                    const float off = MODE == 0 ? m : sStats[kb * kPvKB + c * kPvKC + j];
+                    const float p = exp2f(fmaf(t[c * kPvKC + j], sc, -off));
+                    l += p;
+                    hi[j] = p;
+                    lo[j] = lo_tf32(p);
                 }
-                mbar_wait(&bars.pv_empty[s], (use & 1) ^ 1);
-                float* ph_s = sPh(s);
-                float* pl_s = sPl(s);
-#pragma unroll
-                for (int q4 = 0; q4 < kTcKC / 4; ++q4) {
-                    *reinterpret_cast<float4*>(ph_s + (q4 * kTcM + r) * 4) = ph[q4];
-                    *reinterpret_cast<float4*>(pl_s + (q4 * kTcM + r) * 4) = pl[q4];
-                }
-                fence_async_smem();
-                mbar_arrive(&bars.pv_full[s]);
+                const int slot = gc & 1;
+                mbar_wait(&bars.p_empty[slot], ((gc >> 1) & 1) ^ 1);
+                tc_fence_after();
+                tmem_st16(trow + kPvPCol + slot * 32, hi);
+                tmem_st16(trow + kPvPCol + slot * 32 + 16, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars.p_full[slot]);
             }
         }
 
-        // ---- epilogue: y = gamma * O + x ----
-        const float gamma = __ldg(gamma_p);
+        // ---- epilogue, part 1: accumulator rows -> shared memory (the operand buffers are free) ----
         mbar_wait(&bars.o_full, 0);
         tc_fence_after();
-        const float* xr = x + ((int64_t)b * g.N + i0 + r) * g.x_s;
-        float* yr = y + ((int64_t)b * g.N + i0 + r) * g.y_s;
-        for (int cc = 0; cc < g.Cp; cc += 16) {
-            float o[16];
-            tmem_ld16(trow + kTcOCol + cc, o);
+        const float rs = MODE == 0 ? 1.f / l : 1.f;
+        if (MODE == 0) a.lse[(int64_t)b * g.N + r0 + r] = (m + log2f(l)) * kLn2;
+        float* trow_s = reinterpret_cast<float*>(smem) + (size_t)r * (g.Cp + 4);
+        for (int cc = 0; cc < g.Cp; cc += 32) {
+            float o[32];
+            tmem_ld32(trow + kPvOCol + cc, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const int c = cc + 4 * q4;
-                if (c < g.C) {
-                    const float4 xi = ld4(xr + c);
-                    float4 out;
-                    out.x = fmaf(gamma, o[4 * q4 + 0], xi.x);
-                    out.y = fmaf(gamma, o[4 * q4 + 1], xi.y);
-                    out.z = fmaf(gamma, o[4 * q4 + 2], xi.z);
-                    out.w = fmaf(gamma, o[4 * q4 + 3], xi.w);
-                    *reinterpret_cast<float4*>(yr + c) = out;
-                }
-            }
+            for (int q4 = 0; q4 < 8; ++q4)
+                *reinterpret_cast<float4*>(trow_s + cc + 4 * q4) =
+                    make_float4(o[4 * q4] * rs, o[4 * q4 + 1] * rs, o[4 * q4 + 2] * rs, o[4 * q4 + 3] * rs);
         }
         tc_fence_before();
-    } else if (warp < 8) {
+    } else if (warp < 6) {
         // =====================================================================
-        // loader warps
+        // lo pass of X and of the Y blocks
         // =====================================================================
         const int lt = tid - 128;
-        uint32_t n_k = 0;                       // K blocks loaded so far
-        auto load_k = [&](int kb) {
-            if (n_k > 0) mbar_wait(&bars.k_empty, (n_k - 1) & 1);
-            load_kmajor_tile(Kb + (int64_t)kb * kTcKB * g.k_s, g.k_s, d4, sKh, sKl, lt);
+        mbar_wait(&bars.x_full, 0);
+        lo_pass(sXr, sXl, kTileBytes / 16, lt, 64);
+        fence_async_smem();
+        mbar_arrive(&bars.x_ready);
+        for (int u = 0; u < nuse; ++u) {
+            const int buf = u & 1;
+            mbar_wait(&bars.y_full[buf], (u >> 1) & 1);
+            lo_pass(sYr(buf), sYl(buf), kTileBytes / 16, lt, 64);
             fence_async_smem();
-            mbar_arrive(&bars.k_full);
-            ++n_k;
-        };
-        load_kmajor_tile(Qb, g.q_s, d4, sQh, sQl, lt);
-        for (int kb = 0; kb < nkb; ++kb) load_k(kb);          // pass A
-        load_k(0);                                             // pass B, first block
-        uint32_t gchunk = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-            for (int c = 0; c < kTcChunks; ++c, ++gchunk) {
-                const int s = gchunk % g.stages;
-                const uint32_t use = gchunk / g.stages;
-                mbar_wait(&bars.pv_empty[s], (use & 1) ^ 1);
-                load_v_chunk(Vb + (int64_t)(kb * kTcKB + c * kTcKC) * g.v_s, g.v_s, C4, g.Cp, sVh(s), sVl(s), lt);
-                fence_async_smem();
-                mbar_arrive(&bars.pv_full[s]);
-                if (c == 1 && kb + 1 < nkb) load_k(kb + 1);    // prefetch the next key block
+            mbar_arrive(&bars.y_ready[buf]);
+        }
+    } else if (warp < 8) {
+        // =====================================================================
+        // lo pass of the W chunks
+        // =====================================================================
+        const int lt = tid - 192;
+        for (int gc = 0; gc < nchunks; ++gc) {
+            const int s = gc % g.stages;
+            mbar_wait(&bars.w_full[s], (gc / g.stages) & 1);
+            lo_pass(sWr(s), sWl(s), w_bytes / 16, lt, 64);
+            fence_async_smem();
+            mbar_arrive(&bars.w_ready[s]);
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {                                   // TMA producer: X tile, then the Y blocks
+            mbar_expect_tx(&bars.x_full, kTileBytes);
+            tma_load_3d(sXr, &tmX, 0, r0, b, &bars.x_full);
+            for (int u = 0; u < nuse; ++u) {
+                const int buf = u & 1;
+                if (u >= 2) mbar_wait(&bars.y_empty[buf], ((u >> 1) - 1) & 1);
+                mbar_expect_tx(&bars.y_full[buf], kTileBytes);
+                tma_load_3d(sYr(buf), &tmY, 0, (u % g.nkb) * kPvKB, b, &bars.y_full[buf]);
             }
         }
+        __syncwarp();
+    } else if (warp == 9) {
+        if (lane == 0) {                                   // TMA producer: W chunks
+            const int nblk = g.Cp / 32;
+            for (int gc = 0; gc < nchunks; ++gc) {
+                const int s = gc % g.stages;
+                if (gc >= g.stages) mbar_wait(&bars.w_empty[s], ((gc / g.stages) - 1) & 1);
+                mbar_expect_tx(&bars.w_full[s], w_bytes);
+                for (int k = 0; k < nblk; ++k)
+                    tma_load_3d(sWr(s) + k * blk_bytes, &tmW, k * 32, gc * kPvKC, b, &bars.w_full[s]);
+            }
+        }
+        __syncwarp();
     } else {
-      if (lane == 0) {
-        // =====================================================================
-        // MMA issuer (one thread)
-        // =====================================================================
-        const uint32_t idesc_s = idesc_tf32(kTcM, kTcKB, false, false);
-        const uint32_t idesc_o1 = idesc_tf32(kTcM, g.n1, false, false);
-        const uint32_t idesc_o2 = idesc_tf32(kTcM, g.n2 > 0 ? g.n2 : 16, false, false);
-        const uint32_t lbo_k = kTcM * 16, sbo = 128;            // K-major tiles with 128 rows
-        const uint32_t aQh = smem_u32(sQh), aQl = smem_u32(sQl), aKh = smem_u32(sKh), aKl = smem_u32(sKl);
-        const int ksteps = g.d >> 3;
-        uint32_t n_k = 0, n_s = 0;
-        auto issue_s = [&]() {
-            mbar_wait(&bars.k_full, n_k & 1);
-            ++n_k;
-            if (n_s > 0) mbar_wait(&bars.s_empty, (n_s - 1) & 1);
-            ++n_s;
-            tc_fence_after();
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t o = ks * 2 * lbo_k;
-                const uint64_t qh = smem_desc(aQh + o, lbo_k, sbo), ql = smem_desc(aQl + o, lbo_k, sbo);
-                const uint64_t kh = smem_desc(aKh + o, lbo_k, sbo), kl = smem_desc(aKl + o, lbo_k, sbo);
-                mma_tf32(tmem, ql, kh, idesc_s, ks > 0);
-                mma_tf32(tmem, qh, kl, idesc_s, true);
-                mma_tf32(tmem, qh, kh, idesc_s, true);
-            }
-            tc_commit(&bars.k_empty);
-            tc_commit(&bars.s_full);
-        };
-        for (int kb = 0; kb < nkb; ++kb) issue_s();            // pass A
-        const uint32_t lbo_v = g.Cp * 16;                     // V tile: K-major with Cp rows
-        uint32_t gchunk = 0;
-        for (int kb = 0; kb < nkb; ++kb) {                      // pass B
-            issue_s();
-            for (int c = 0; c < kTcChunks; ++c, ++gchunk) {
-                const int s = gchunk % g.stages;
-                const uint32_t use = gchunk / g.stages;
-                mbar_wait(&bars.pv_full[s], use & 1);
+        if (lane == 0) {
+            // =================================================================
+            // MMA issuer (one thread)
+            // =================================================================
+            const uint32_t idesc_s = idesc_tf32(kPvM, kPvKB, false, false);
+            const uint32_t idesc_o1 = idesc_tf32(kPvM, g.n1, false, true);
+            const uint32_t idesc_o2 = idesc_tf32(kPvM, g.n2 > 0 ? g.n2 : 32, false, true);
+            const uint32_t aXr = smem_u32(sXr), aXl = smem_u32(sXl);
+            uint32_t n_s = 0;
+            auto issue_s = [&](int u) {
+                const int buf = u & 1;
+                mbar_wait(&bars.y_full[buf], (u >> 1) & 1);
+                mbar_wait(&bars.y_ready[buf], (u >> 1) & 1);
+                if (n_s > 0) mbar_wait(&bars.s_empty, (n_s - 1) & 1);
+                ++n_s;
                 tc_fence_after();
-                const uint32_t aPh = smem_u32(sPh(s)), aPl = smem_u32(sPl(s));
-                const uint32_t aVh = smem_u32(sVh(s)), aVl = smem_u32(sVl(s));
-#pragma unroll
-                for (int ks = 0; ks < kTcKC / 8; ++ks) {
-                    const uint32_t po = ks * 2 * lbo_k, vo = ks * 2 * lbo_v;
-                    const uint64_t ph = smem_desc(aPh + po, lbo_k, sbo), pl = smem_desc(aPl + po, lbo_k, sbo);
-                    const bool acc = (gchunk | ks) != 0;
-                    {
-                        const uint64_t vh = smem_desc(aVh + vo, lbo_v, sbo), vl = smem_desc(aVl + vo, lbo_v, sbo);
-                        mma_tf32(tmem + kTcOCol, pl, vh, idesc_o1, acc);
-                        mma_tf32(tmem + kTcOCol, ph, vl, idesc_o1, true);
-                        mma_tf32(tmem + kTcOCol, ph, vh, idesc_o1, true);
-                    }
-                    if (g.n2 > 0) {
-                        const uint32_t ho = g.n1 * 16;               // row n1 of the V tile
-                        const uint64_t vh = smem_desc(aVh + vo + ho, lbo_v, sbo);
-                        const uint64_t vl = smem_desc(aVl + vo + ho, lbo_v, sbo);
-                        mma_tf32(tmem + kTcOCol + g.n1, pl, vh, idesc_o2, acc);
-                        mma_tf32(tmem + kTcOCol + g.n1, ph, vl, idesc_o2, true);
-                        mma_tf32(tmem + kTcOCol + g.n1, ph, vh, idesc_o2, true);
-                    }
+                const uint32_t aYr = smem_u32(sYr(buf)), aYl = smem_u32(sYl(buf));
+                for (int ks = 0; ks < g.ksteps; ++ks) {
+                    const uint32_t o = ks * 32;
+                    mma_tf32(tmem, desc_kmajor(aXl + o), desc_kmajor(aYr + o), idesc_s, ks > 0);
+                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYl + o), idesc_s, true);
+                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYr + o), idesc_s, true);
                 }
-                tc_commit(&bars.pv_empty[s]);
+                tc_commit(&bars.y_empty[buf]);
+                tc_commit(&bars.s_full);
+            };
+            mbar_wait(&bars.x_full, 0);
+            mbar_wait(&bars.x_ready, 0);
+            int u = 0;
+            if (MODE == 0)
+                for (int kb = 0; kb < g.nkb; ++kb) issue_s(u++);           // pass A
+            issue_s(u++);                                                   // pass B, first block
+            uint32_t gc = 0;
+            const uint32_t half_off = (uint32_t)(g.n1 / 32) * blk_bytes;    // first block of the 2nd N half
+            for (int kb = 0; kb < g.nkb; ++kb) {
+                if (kb + 1 < g.nkb) issue_s(u++);                           // next block's S while P*V runs
+                for (int c = 0; c < kPvChunks; ++c, ++gc) {
+                    const int s = gc % g.stages, slot = gc & 1;
+                    mbar_wait(&bars.w_full[s], (gc / g.stages) & 1);
+                    mbar_wait(&bars.w_ready[s], (gc / g.stages) & 1);
+                    mbar_wait(&bars.p_full[slot], (gc >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t aWr = smem_u32(sWr(s)), aWl = smem_u32(sWl(s));
+#pragma unroll
+                    for (int ks = 0; ks < kPvKC / 8; ++ks) {
+                        const uint32_t ph = tmem + kPvPCol + slot * 32 + ks * 8, pl = ph + 16;
+                        const uint32_t wo = ks * 1024;
+                        const bool acc = (gc | ks) != 0;
+                        mma_tf32_ts(tmem + kPvOCol, pl, desc_mnmajor(aWr + wo, blk_bytes), idesc_o1, acc);
+                        mma_tf32_ts(tmem + kPvOCol, ph, desc_mnmajor(aWl + wo, blk_bytes), idesc_o1, true);
+                        mma_tf32_ts(tmem + kPvOCol, ph, desc_mnmajor(aWr + wo, blk_bytes), idesc_o1, true);
+                        if (g.n2 > 0) {
+                            const uint32_t w2 = wo + half_off;
+                            mma_tf32_ts(tmem + kPvOCol + g.n1, pl, desc_mnmajor(aWr + w2, blk_bytes), idesc_o2, acc);
+                            mma_tf32_ts(tmem + kPvOCol + g.n1, ph, desc_mnmajor(aWl + w2, blk_bytes), idesc_o2, true);
+                            mma_tf32_ts(tmem + kPvOCol + g.n1, ph, desc_mnmajor(aWr + w2, blk_bytes), idesc_o2, true);
+                        }
+                    }
+                    tc_commit(&bars.w_empty[s]);
+                    tc_commit(&bars.p_empty[slot]);
+                }
             }
+            tc_commit(&bars.o_full);
+            tc_fence_before();
         }
-        tc_commit(&bars.o_full);
-        tc_fence_before();
-      }
-      __syncwarp();
+        __syncwarp();
     }
 
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 10) {
         tc_fence_after();
-        tmem_dealloc(tmem, kTcTmemCols);
+        tmem_dealloc(tmem, 512);
+    }
+    // ---- epilogue, part 2: every thread streams the staged tile out with coalesced accesses ----
+    {
+        const float gamma = __ldg(a.gamma);
+        const int C4 = g.C >> 2, ld = g.Cp + 4;
+        const float* tile = reinterpret_cast<const float*>(smem);
+        const int64_t row0 = (int64_t)b * g.N + r0;
+        for (int idx = tid; idx < kPvM * C4; idx += kPvThreads) {
+            const int rr = idx / C4, c = (idx - rr * C4) * 4;
+            const float4 o = *reinterpret_cast<const float4*>(tile + (size_t)rr * ld + c);
+            if (MODE == 0) {
+                const float4 xi = ld_stream4(a.x + (row0 + rr) * a.x_s + c);
+                st_stream4(a.y + (row0 + rr) * a.y_s + c,
+                           make_float4(fmaf(gamma, o.x, xi.x), fmaf(gamma, o.y, xi.y), fmaf(gamma, o.z, xi.z),
+                                       fmaf(gamma, o.w, xi.w)));
+                if (a.o_save) st_stream4(a.o_save + (row0 + rr) * a.o_s + c, o);
+            } else {
+                st_stream4(a.out + (row0 + rr) * a.out_s + c,
+                           make_float4(gamma * o.x, gamma * o.y, gamma * o.z, gamma * o.w));
+            }
+        }
+    }
+}
+
+// =============================================================================
+// Gradient w.r.t. the row operand: dX = gamma * scale * dS Y with
+//   dS_ij = P_ij (dp_ij - E_i),  dp = U W^T,  P from (X, Y, lse),  E_i = <dy_i, O_i>.
+//   MODE 0: dQ  (X = Q rows, Y = K blocks, U = dy rows, W = V blocks; lse/E per ROW)
+//   MODE 1: dK  (X = K rows, Y = Q blocks, U = V rows,  W = dy blocks; lse/E per COLUMN)
+// Per column block of 128: S = X Y^T and dp (K dimension = channels, streamed in 32-channel
+// chunks through a 2-stage TMA ring) land in TMEM columns [0,128) and [128,256); the softmax
+// warps overwrite them in place with dS (hi | lo), which then feeds dX += dS Y as a
+// TMEM-resident A operand (Y re-read MN-major).  dX accumulates in columns [256,288).
+// =============================================================================
+constexpr int kDsThreads = 384;
+constexpr int kDsOCol = 256;
+constexpr int kDsFixedBytes = 6 * kTileBytes;    // X, Y (K-major), Y (MN-major): raw + lo each
+constexpr int kDsStageBytes = 4 * kTileBytes;    // U raw/lo + W raw/lo
+
+struct DsGeom {
+    int N, d, C, nkb, nch, ksteps, last_ksteps;  // nch = channel chunks of 32; k-steps of the last one
+};
+
+struct DsArgs {
+    const float* lse; const float* E;            // [B,N] each
+    float* out; int64_t out_s;                    // dX rows
+    float* dscale;                                // one float, accumulated (MODE 0 only; may be null)
+    const float* scale; const float* gamma;
+};
+
+struct DsBars {
+    uint64_t x_full, x_ready;
+    uint64_t y_full, y_ready, y_empty;
+    uint64_t ymn_full, ymn_ready, ymn_empty;
+    uint64_t uw_full[2], uw_ready[2], uw_empty[2];
+    uint64_t sd_full, ds_full, o_full;
+    uint32_t tmem_base;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kDsThreads, 1)
+nl_ds_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmYmn, const __grid_constant__ CUtensorMap tmU,
+             const __grid_constant__ CUtensorMap tmW, const DsArgs a, const DsGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ DsBars bars;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, r0 = blockIdx.x * kPvM;
+
+    uint8_t* sXr = smem;
+    uint8_t* sXl = smem + kTileBytes;
+    uint8_t* sYr = smem + 2 * kTileBytes;
+    uint8_t* sYl = smem + 3 * kTileBytes;
+    uint8_t* sMr = smem + 4 * kTileBytes;          // Y again, MN-major swizzle
+    uint8_t* sMl = smem + 5 * kTileBytes;
+    auto sU = [&](int s) { return smem + kDsFixedBytes + s * kDsStageBytes; };   // raw, +16K lo
+    auto sW = [&](int s) { return smem + kDsFixedBytes + s * kDsStageBytes + 2 * kTileBytes; };
+
+    if (tid == 0) {
+        mbar_init(&bars.x_full, 1);   mbar_init(&bars.x_ready, 32);
+        mbar_init(&bars.y_full, 1);   mbar_init(&bars.y_ready, 32);   mbar_init(&bars.y_empty, 1);
+        mbar_init(&bars.ymn_full, 1); mbar_init(&bars.ymn_ready, 32); mbar_init(&bars.ymn_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.uw_full[i], 1);
+            mbar_init(&bars.uw_ready[i], 128);
+            mbar_init(&bars.uw_empty[i], 1);
+        }
+        mbar_init(&bars.sd_full, 1);
+        mbar_init(&bars.ds_full, 128);
+        mbar_init(&bars.o_full, 1);
+        mbar_init_fence();
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmYmn);
+        tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmW);
+    }
+    if (warp == 11) tmem_alloc(&bars.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars.tmem_base;
+
+    if (warp < 4) {
+        // ---- softmax / dS warps: thread r <-> row r0 + r <-> TMEM lane r ----
+        const int r = tid;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const float scale = a.scale ? __ldg(a.scale) : 1.f;
+        const float sc = scale * kLog2e;
+        const int64_t row = (int64_t)b * g.N + r0 + r;
+        const float* lse_b = a.lse + (int64_t)b * g.N;
+        const float* E_b = a.E + (int64_t)b * g.N;
+        float lse_r = 0.f, E_r = 0.f;
+        if (MODE == 0) { lse_r = __ldg(a.lse + row) * kLog2e; E_r = __ldg(a.E + row); }
+        float dsc = 0.f;
+        for (int cb = 0; cb < g.nkb; ++cb) {
+            mbar_wait(&bars.sd_full, cb & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c32 = 0; c32 < kPvKB / 32; ++c32) {
+                float sv[32], dp[32];
+                tmem_ld32(trow + c32 * 32, sv);
+                tmem_ld32(trow + 128 + c32 * 32, dp);
+                tmem_ld_wait();
+                float hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float lj = lse_r, ej = E_r;
+                    if (MODE == 1) {
+                        const int col = cb * kPvKB + c32 * 32 + j;
+                        lj = __ldg(lse_b + col) * kLog2e;
+                        ej = __ldg(E_b + col);
+                    }
+                    const float p = exp2f(fmaf(sv[j], sc, -lj));
+                    const float ds = p * (dp[j] - ej);
+                    dsc = fmaf(ds, sv[j], dsc);
+                    hi[j] = ds;
+                    lo[j] = lo_tf32(ds);
+                }
+                tmem_st16(trow + c32 * 32, hi);
+                tmem_st16(trow + c32 * 32 + 16, hi + 16);
+                tmem_st16(trow + 128 + c32 * 32, lo);
+                tmem_st16(trow + 128 + c32 * 32 + 16, lo + 16);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.ds_full);
+        }
+        const float gs = __ldg(a.gamma) * scale;
+        if (MODE == 0 && a.dscale) {
+            dsc = group_sum<32>(dsc);
+            if (lane == 0) atomicAdd(a.dscale, dsc * __ldg(a.gamma));
+        }
+        mbar_wait(&bars.o_full, 0);
+        tc_fence_after();
+        float o[32];
+        tmem_ld32(trow + kDsOCol, o);
+        tmem_ld_wait();
+        float* orow = a.out + row * a.out_s;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+            if (4 * q4 < g.d)
+                *reinterpret_cast<float4*>(orow + 4 * q4) =
+                    make_float4(gs * o[4 * q4], gs * o[4 * q4 + 1], gs * o[4 * q4 + 2], gs * o[4 * q4 + 3]);
+        tc_fence_before();
+    } else if (warp < 8) {
+        // ---- lo pass of the U / W channel chunks ----
+        const int lt = tid - 128;
+        const int total = g.nkb * g.nch;
+        for (int gch = 0; gch < total; ++gch) {
+            const int s = gch & 1;
+            mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
+            lo_pass(sU(s), sU(s) + kTileBytes, kTileBytes / 16, lt, 128);
+            lo_pass(sW(s), sW(s) + kTileBytes, kTileBytes / 16, lt, 128);
+            fence_async_smem();
+            mbar_arrive(&bars.uw_ready[s]);
+        }
+    } else if (warp == 8) {
+        // ---- lo pass of X and of the two images of each Y block ----
+        mbar_wait(&bars.x_full, 0);
+        lo_pass(sXr, sXl, kTileBytes / 16, lane, 32);
+        fence_async_smem();
+        mbar_arrive(&bars.x_ready);
+        for (int cb = 0; cb < g.nkb; ++cb) {
+            mbar_wait(&bars.y_full, cb & 1);
+            lo_pass(sYr, sYl, kTileBytes / 16, lane, 32);
+            fence_async_smem();
+            mbar_arrive(&bars.y_ready);
+            mbar_wait(&bars.ymn_full, cb & 1);
+            lo_pass(sMr, sMl, kTileBytes / 16, lane, 32);
+            fence_async_smem();
+            mbar_arrive(&bars.ymn_ready);
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {                                   // TMA: X, then both images of every Y block
+            mbar_expect_tx(&bars.x_full, kTileBytes);
+            tma_load_3d(sXr, &tmX, 0, r0, b, &bars.x_full);
+            for (int cb = 0; cb < g.nkb; ++cb) {
+                if (cb > 0) mbar_wait(&bars.y_empty, (cb - 1) & 1);
+                mbar_expect_tx(&bars.y_full, kTileBytes);
+                tma_load_3d(sYr, &tmY, 0, cb * kPvKB, b, &bars.y_full);
+                if (cb > 0) mbar_wait(&bars.ymn_empty, (cb - 1) & 1);
+                mbar_expect_tx(&bars.ymn_full, kTileBytes);
+                tma_load_3d(sMr, &tmYmn, 0, cb * kPvKB, b, &bars.ymn_full);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        if (lane == 0) {                                   // TMA: U / W channel chunks
+            int gch = 0;
+            for (int cb = 0; cb < g.nkb; ++cb)
+                for (int ch = 0; ch < g.nch; ++ch, ++gch) {
+                    const int s = gch & 1;
+                    if (gch >= 2) mbar_wait(&bars.uw_empty[s], ((gch >> 1) - 1) & 1);
+                    mbar_expect_tx(&bars.uw_full[s], 2 * kTileBytes);
+                    tma_load_3d(sU(s), &tmU, ch * 32, r0, b, &bars.uw_full[s]);
+                    tma_load_3d(sW(s), &tmW, ch * 32, cb * kPvKB, b, &bars.uw_full[s]);
+                }
+        }
+        __syncwarp();
+    } else {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            const uint32_t idesc_s = idesc_tf32(kPvM, kPvKB, false, false);
+            const uint32_t idesc_o = idesc_tf32(kPvM, 32, false, true);
+            const uint32_t aXr = smem_u32(sXr), aXl = smem_u32(sXl), aYr = smem_u32(sYr), aYl = smem_u32(sYl);
+            const uint32_t aMr = smem_u32(sMr), aMl = smem_u32(sMl);
+            mbar_wait(&bars.x_full, 0);
+            mbar_wait(&bars.x_ready, 0);
+            int gch = 0;
+            for (int cb = 0; cb < g.nkb; ++cb) {
+                mbar_wait(&bars.y_full, cb & 1);
+                mbar_wait(&bars.y_ready, cb & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < g.ksteps; ++ks) {
+                    const uint32_t o = ks * 32;
+                    mma_tf32(tmem, desc_kmajor(aXl + o), desc_kmajor(aYr + o), idesc_s, ks > 0);
+                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYl + o), idesc_s, true);
+                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYr + o), idesc_s, true);
+                }
+                tc_commit(&bars.y_empty);
+                for (int ch = 0; ch < g.nch; ++ch, ++gch) {
+                    const int s = gch & 1;
+                    mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
+                    mbar_wait(&bars.uw_ready[s], (gch >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t aUr = smem_u32(sU(s)), aUl = aUr + kTileBytes;
+                    const uint32_t aWr = smem_u32(sW(s)), aWl = aWr + kTileBytes;
+                    const int nks = ch == g.nch - 1 ? g.last_ksteps : 4;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t o = ks * 32;
+                        mma_tf32(tmem + 128, desc_kmajor(aUl + o), desc_kmajor(aWr + o), idesc_s, (ch | ks) != 0);
+                        mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWl + o), idesc_s, true);
+                        mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWr + o), idesc_s, true);
+                    }
+                    tc_commit(&bars.uw_empty[s]);
+                }
+                tc_commit(&bars.sd_full);
+                mbar_wait(&bars.ds_full, cb & 1);
+                mbar_wait(&bars.ymn_full, cb & 1);
+                mbar_wait(&bars.ymn_ready, cb & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < kPvKB / 8; ++ks) {
+                    const uint32_t dh = tmem + ks * 8, dl = tmem + 128 + ks * 8;
+                    const uint32_t o = ks * 1024;
+                    mma_tf32_ts(tmem + kDsOCol, dl, desc_mnmajor(aMr + o, kTileBytes), idesc_o, (cb | ks) != 0);
+                    mma_tf32_ts(tmem + kDsOCol, dh, desc_mnmajor(aMl + o, kTileBytes), idesc_o, true);
+                    mma_tf32_ts(tmem + kDsOCol, dh, desc_mnmajor(aMr + o, kTileBytes), idesc_o, true);
+                }
+                tc_commit(&bars.ymn_empty);
+            }
+            tc_commit(&bars.o_full);
+            tc_fence_before();
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    if (warp == 11) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// E[b,i] = <dy[b,i,:], O[b,i,:]> (one warp per row); dgamma += sum E
+__global__ void __launch_bounds__(256)
+nl_rowdot_kernel(const float* __restrict__ dy, const float* __restrict__ O, float* __restrict__ E,
+                 float* __restrict__ dgamma, int64_t rows, int C4, int64_t dy_s, int64_t o_s) {
+    __shared__ float red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    float e = 0.f;
+    if (row < rows) {
+        const float* a = dy + row * dy_s;
+        const float* o = O + row * o_s;
+        for (int c = lane; c < C4; c += 32) e += dot4(ld_stream4(a + 4 * c), ld_stream4(o + 4 * c));
+        e = group_sum<32>(e);
+        if (lane == 0) E[row] = e;
+    }
+    if (lane == 0) red[warp] = row < rows ? e : 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(dgamma, t);
     }
 }
 
 // ---- host side ----------------------------------------------------------------
 
-static bool tc_geom(int N, int d, int C, TcGeom& g) {
-    if (N % kTcKB || N < kTcKB || d % 8 || d < 8 || d > 32 || C % 4 || C < 16 || C > 320) return false;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    // resolved once; immutable afterwards (the driver entry point, no -lcuda link dependency)
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// [batch, rows, inner] fp32 tensor with a uniform row stride (floats); box = [32 floats x box_rows].
+// mn_major selects the 32-byte-atom swizzle the MN-major tf32 operand layout needs.
+int make_tmap_rows(CUtensorMap* tm, const float* base, int inner, int rows, int batch, int64_t row_stride,
+                   int box_rows, bool mn_major) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return DAVI_ECUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)rows * (cuuint64_t)row_stride * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for inner=%d rows=%d batch=%d stride=%lld", (int)r, inner, rows,
+                  batch, (long long)row_stride);
+        return DAVI_ECUDA;
+    }
+    return DAVI_OK;
+}
+
+static bool pv_geom(int N, int d, int C, bool stats_in_smem, PvGeom& g) {
+    if (N % kPvKB || N < kPvKB || d % 4 || d < 4 || d > 32 || C % 4 || C < 4 || C > 320) return false;
     g.N = N; g.d = d; g.C = C;
-    g.Cp = (C + 15) / 16 * 16;
+    g.Cp = (C + 31) / 32 * 32;
+    g.nkb = N / kPvKB;
     if (g.Cp <= 256) { g.n1 = g.Cp; g.n2 = 0; }
-    else { g.n1 = ((g.Cp / 2) + 15) / 16 * 16; g.n2 = g.Cp - g.n1; }
-    const int fixed = 4 * kTcM * d * 4;
-    const int stage = 2 * kTcM * kTcKC * 4 + 2 * kTcKC * g.Cp * 4;
-    int stages = (227 * 1024 - 1024 - fixed) / stage;
-    if (stages > kTcMaxStages) stages = kTcMaxStages;
+    else { g.n1 = 160; g.n2 = g.Cp - 160; }
+    g.ksteps = (d + 7) / 8;
+    const int stage = 2 * kPvKC * g.Cp * 4;
+    const int avail = 227 * 1024 - 1024 - kPvFixedBytes - (stats_in_smem ? N * 4 : 0);
+    int stages = avail / stage;
+    if (stages > kPvMaxStages) stages = kPvMaxStages;
     if (stages < 2) return false;
     g.stages = stages;
     return true;
 }
 
 bool nonlocal_tc_supported(int B, int N, int d, int C) {
-    TcGeom g;
-    return B > 0 && tc_geom(N, d, C, g);
+    PvGeom g;
+    return B > 0 && B <= 65535 && pv_geom(N, d, C, true, g);
+}
+
+template <int MODE>
+static int pv_launch(const char* fn, const float* X, const float* Y, const float* W, int64_t x_s, int64_t y_s,
+                     int64_t w_s, const PvArgs& a, int B, int N, int d, int C, cudaStream_t st) {
+    PvGeom g;
+    if (!pv_geom(N, d, C, MODE == 1, g)) {
+        set_error("%s: shape not supported by the tensor-core kernel", fn);
+        return DAVI_EINVAL;
+    }
+    CUtensorMap tmX, tmY, tmW;
+    int rc;
+    if ((rc = make_tmap_rows(&tmX, X, d, N, B, x_s, kPvM, false))) return rc;
+    if ((rc = make_tmap_rows(&tmY, Y, d, N, B, y_s, kPvKB, false))) return rc;
+    if ((rc = make_tmap_rows(&tmW, W, C, N, B, w_s, kPvKC, true))) return rc;
+    const size_t smem = 1024 + (size_t)kPvFixedBytes + (size_t)g.stages * 2 * kPvKC * g.Cp * 4 +
+                        (MODE == 1 ? (size_t)N * 4 : 0);
+    DAVI_CUDA(cudaFuncSetAttribute(nl_pv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nl_pv_kernel<MODE><<<dim3(N / kPvM, B), kPvThreads, smem, st>>>(tmX, tmY, tmW, a, g);
+    return check_launch(fn);
 }
 
 int nonlocal_fwd_tc_launch(const float* Q, const float* K, const float* V, const float* x, float* y,
-                           float* lse, int B, int N, int d, int C, int64_t q_s, int64_t k_s, int64_t v_s,
-                           int64_t x_s, int64_t y_s, const float* scale, const float* gamma, cudaStream_t st) {
-    TcGeom g;
-    if (!tc_geom(N, d, C, g)) {
-        set_error("davi_nonlocal_attn_fwd: shape not supported by the tensor-core kernel");
-        return DAVI_EINVAL;
-    }
-    g.q_s = q_s; g.k_s = k_s; g.v_s = v_s; g.x_s = x_s; g.y_s = y_s;
-    const size_t smem = (size_t)4 * kTcM * d * 4 +
-                        (size_t)g.stages * (2 * kTcM * kTcKC * 4 + 2 * kTcKC * g.Cp * 4);
-    DAVI_CUDA(cudaFuncSetAttribute(nonlocal_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nonlocal_fwd_tc<<<dim3(N / kTcM, B), kTcThreads, smem, st>>>(Q, K, V, x, y, lse, scale, gamma, g);
-    return check_launch("davi_nonlocal_attn_fwd");
+                           float* lse, float* o_save, int B, int N, int d, int C, int64_t q_s, int64_t k_s,
+                           int64_t v_s, int64_t x_s, int64_t y_s, int64_t o_s, const float* scale,
+                           const float* gamma, cudaStream_t st) {
+    PvArgs a{};
+    a.x = x; a.y = y; a.o_save = o_save; a.lse = lse;
+    a.x_s = x_s; a.y_s = y_s; a.o_s = o_s;
+    a.scale = scale; a.gamma = gamma;
+    return pv_launch<0>("davi_nonlocal_attn_fwd", Q, K, V, q_s, k_s, v_s, a, B, N, d, C, st);
+}
+
+// dV = gamma * P^T dy with P recomputed from (K, Q, lse): rows = keys, column blocks = queries
+int nonlocal_dv_tc_launch(const float* Q, const float* K, const float* lse, const float* dy, float* dV, int B,
+                          int N, int d, int C, int64_t q_s, int64_t k_s, int64_t dy_s, int64_t dv_s,
+                          const float* scale, const float* gamma, cudaStream_t st) {
+    PvArgs a{};
+    a.lse_in = lse; a.out = dV; a.out_s = dv_s;
+    a.scale = scale; a.gamma = gamma;
+    return pv_launch<1>("davi_nonlocal_attn_bwd(dV)", K, Q, dy, k_s, q_s, dy_s, a, B, N, d, C, st);
+}
+
+
+template <int MODE>
+static int ds_launch(const char* fn, const float* X, const float* Y, const float* U, const float* W, int64_t x_s,
+                     int64_t y_s, int64_t u_s, int64_t w_s, const DsArgs& a, int B, int N, int d, int C,
+                     cudaStream_t st) {
+    DsGeom g;
+    g.N = N; g.d = d; g.C = C; g.nkb = N / kPvKB;
+    g.nch = (C + 31) / 32;
+    g.ksteps = (d + 7) / 8;
+    g.last_ksteps = (C - 32 * (g.nch - 1) + 7) / 8;
+    CUtensorMap tmX, tmY, tmYmn, tmU, tmW;
+    int rc;
+    if ((rc = make_tmap_rows(&tmX, X, d, N, B, x_s, kPvM, false))) return rc;
+    if ((rc = make_tmap_rows(&tmY, Y, d, N, B, y_s, kPvKB, false))) return rc;
+    if ((rc = make_tmap_rows(&tmYmn, Y, d, N, B, y_s, kPvKB, true))) return rc;
+    if ((rc = make_tmap_rows(&tmU, U, C, N, B, u_s, kPvM, false))) return rc;
+    if ((rc = make_tmap_rows(&tmW, W, C, N, B, w_s, kPvKB, false))) return rc;
+    const size_t smem = 1024 + (size_t)kDsFixedBytes + 2 * (size_t)kDsStageBytes;
+    DAVI_CUDA(cudaFuncSetAttribute(nl_ds_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nl_ds_kernel<MODE><<<dim3(N / kPvM, B), kDsThreads, smem, st>>>(tmX, tmY, tmYmn, tmU, tmW, a, g);
+    return check_launch(fn);
+}
+
+// Full gradient on the tensor cores.  E: workspace [B,N]; dgs = {dgamma, dscale} (overwritten).
+int nonlocal_bwd_tc_launch(const float* Q, const float* K, const float* V, const float* lse, const float* O,
+                           const float* dy, float* dQ, float* dK, float* dV, float* dgs, int B, int N, int d,
+                           int C, int64_t q_s, int64_t k_s, int64_t v_s, int64_t o_s, int64_t dy_s,
+                           const float* scale, const float* gamma, float* E, cudaStream_t st) {
+    const char* fn = "davi_nonlocal_attn_bwd";
+    DAVI_CUDA(cudaMemsetAsync(dgs, 0, 2 * sizeof(float), st));
+    const int64_t rows = (int64_t)B * N;
+    nl_rowdot_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dy, O, E, dgs, rows, C / 4, dy_s, o_s);
+    int rc = check_launch(fn);
+    if (rc) return rc;
+    rc = nonlocal_dv_tc_launch(Q, K, lse, dy, dV, B, N, d, C, q_s, k_s, dy_s, v_s, scale, gamma, st);
+    if (rc) return rc;
+    DsArgs a{};
+    a.lse = lse; a.E = E; a.scale = scale; a.gamma = gamma;
+    a.out = dQ; a.out_s = q_s; a.dscale = dgs + 1;
+    rc = ds_launch<0>(fn, Q, K, dy, V, q_s, k_s, dy_s, v_s, a, B, N, d, C, st);
+    if (rc) return rc;
+    a.out = dK; a.out_s = k_s; a.dscale = nullptr;
+    return ds_launch<1>(fn, K, Q, V, dy, k_s, q_s, v_s, dy_s, a, B, N, d, C, st);
 }
 
 }  // namespace davi

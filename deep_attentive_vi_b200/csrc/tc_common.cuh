@@ -144,6 +144,88 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "memory");
 }
 
+// ---- swizzled layouts, TMA, TMEM-resident A operands (validated by tools/umma_probe2.cu) --------
+// K-major  SWIZZLE_128B        : tile [rows x 32 tf32]; byte(r,c) = (r/8)*1024 + (r%8)*128 + (((c/4)^(r%8))*16) + (c%4)*4
+//                                descriptor layout 2, SBO = 1024, one k-step (8 tf32) = +32 bytes
+// MN-major SWIZZLE_128B_BASE32B: blocks of 32 contiguous MN elements; block = k rows of 128 bytes,
+//                                byte(k,c) = blk*(rows*128) + k*128 + (((c%32/8)^(k%4))*32) + (c%8)*4
+//                                descriptor layout 1, LBO = rows*128 (next 32-element block), SBO = 512,
+//                                one k-step (8 rows) = +1024 bytes.  (The only MN-major layout of 32-bit operands.)
+// Both are exactly what a TMA box [32 floats x rows] writes with CU_TENSOR_MAP_SWIZZLE_128B /
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The tensor core TRUNCATES fp32 bit patterns to tf32, so the raw
+// tile is its own "hi" part and lo = rna_tf32(v - trunc(v)) is written by a separate elementwise pass.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+
+__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                 uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout & 7) << 61;
+    return d;
+}
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return smem_desc_sw(saddr, 16, 1024, kLayoutSw128); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t block_bytes) {
+    return smem_desc_sw(saddr, block_bytes, 512, kLayoutSw128Base32);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M=128 lanes x 8 columns per k-step) is read from TMEM
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// registers -> TMEM, 32 lanes x 16 consecutive columns (lane = 32*(warp%4) + laneid)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]),
+        "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// TMA: one elected thread arms the barrier with the byte count, then issues box loads
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// lo part of the truncation split: v = trunc_tf32(v) + lo, lo rounded to tf32
+__device__ __forceinline__ float lo_tf32(float v) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+    return __uint_as_float(l);
+}
+__device__ __forceinline__ float4 lo4_tf32(const float4& v) {
+    return make_float4(lo_tf32(v.x), lo_tf32(v.y), lo_tf32(v.z), lo_tf32(v.w));
+}
+
 // fp32 -> (hi, lo) with hi exactly representable in tf32 (round to nearest) and
 // lo = v - hi (exact); hi*hi' + lo*hi' + hi*lo' recovers the fp32 product to ~2^-21.
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {

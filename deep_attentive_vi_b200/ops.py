@@ -242,17 +242,20 @@ class _NonlocalAttn(torch.autograd.Function):
         q, q_s = _rows(q); k, k_s = _rows(k); v, v_s = _rows(v); xr, x_s = _rows(x)
         y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
         lse = torch.empty((B, N), device=x.device, dtype=torch.float32)
+        # copy of O = softmax(.) v for the tensor-core gradient (E_i = <dy_i, O_i>, dgamma)
+        need_o = any(ctx.needs_input_grad)
+        o_save = torch.empty((B, N, C), device=x.device, dtype=torch.float32) if need_o else None
         s_t, s_ptr = _scalar_ptr(scale, x)
         g_t, g_ptr = _scalar_ptr(gamma, x)
-        _lib_call("davi_nonlocal_attn_fwd", _p(q), _p(k), _p(v), _p(xr), _p(y), _p(lse), B, N, d, C,
-                  q_s, k_s, v_s, x_s, C, s_ptr, g_ptr, _stream())
-        ctx.save_for_backward(q, k, v, lse, s_t, g_t)
+        _lib_call("davi_nonlocal_attn_fwd", _p(q), _p(k), _p(v), _p(xr), _p(y), _p(lse), _p(o_save), B, N, d, C,
+                  q_s, k_s, v_s, x_s, C, C, s_ptr, g_ptr, _stream())
+        ctx.save_for_backward(q, k, v, lse, o_save, s_t, g_t)
         ctx.cfg = (B, N, d, C, q_s, k_s, v_s)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        q, k, v, lse, s_t, g_t = ctx.saved_tensors
+        q, k, v, lse, o_save, s_t, g_t = ctx.saved_tensors
         B, N, d, C, q_s, k_s, v_s = ctx.cfg
         dy = dy.contiguous()
         lead = dy.shape[:-1]
@@ -265,8 +268,8 @@ class _NonlocalAttn(torch.autograd.Function):
         dgs = torch.empty(2, device=dy.device, dtype=torch.float32)
         wsb = _lib.load().davi_nonlocal_attn_bwd_workspace_bytes(B, N, d, C)
         ws = torch.empty(max(wsb // 4, 1), device=dy.device, dtype=torch.float32)
-        _lib_call("davi_nonlocal_attn_bwd", _p(q), _p(k), _p(v), _p(lse), _p(dy), _p(dq), _p(dk),
-                  _p(dv), _p(dgs), B, N, d, C, q_s, k_s, v_s, C, _p(s_t), _p(g_t), _p(ws), wsb,
+        _lib_call("davi_nonlocal_attn_bwd", _p(q), _p(k), _p(v), _p(lse), _p(o_save), _p(dy), _p(dq), _p(dk),
+                  _p(dv), _p(dgs), B, N, d, C, q_s, k_s, v_s, C, C, _p(s_t), _p(g_t), _p(ws), wsb,
                   _stream())
         dscale = dgs[1] if (s_t is not None and ctx.needs_input_grad[4]) else None
         dgamma = dgs[0] if ctx.needs_input_grad[5] else None

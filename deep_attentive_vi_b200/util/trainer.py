@@ -108,8 +108,9 @@ class Trainer:
     device memory (input batch, KL weight beta, Adamax step size)."""
 
     def __init__(self, model, hparams=None, device="cuda", world_size=1, rank=0, steps_per_epoch=1250,
-                 use_graph=False, graph_warmup=3):
+                 use_graph=False, graph_warmup=3, use_schedule=True):
         self.model = model
+        self.use_schedule = use_schedule
         self.hp = hparams or get_default_train_hparams()
         self.device = torch.device(device)
         self.world, self.rank = world_size, rank
@@ -118,10 +119,12 @@ class Trainer:
         self.steps_per_epoch = steps_per_epoch
         self.beta = 1.0
         self.lr = self.hp.learning_rate
+        if use_schedule:      # epoch 0 of the reference run: lr = lr_min (warm-up), beta = 0.1 (KL warm-up)
+            self.beta = kl_beta(0, self.hp.kl_warmup_epochs, self.hp.kl_warmup_smooth_start)
         for b in model.buffers():
             assert b.device.type == "cuda", "move the model to the GPU before building the Trainer"
         # device-resident step state (read by the kernels, so a captured graph sees fresh values)
-        self.beta_dev = torch.ones((), device=self.device)
+        self.beta_dev = torch.full((), float(self.beta), device=self.device)
         self.hyper_dev = torch.tensor([0.0, 1.0], device=self.device)   # [lr / (1 - b1^t), grad_scale]
         self.lr_dev = torch.full((1,), float(self.lr), device=self.device)
         self.step_dev = torch.zeros(1, device=self.device)              # t, advanced on the device
@@ -130,6 +133,9 @@ class Trainer:
         self._graph = None
         self._static = None
         self.graph_launches = 0
+        # capture needs every autograd node (AccumulateGrad included) to have been created on a
+        # non-default stream: the eager warm-up steps of a graphed trainer run on this side stream
+        self._side = torch.cuda.Stream(device=self.device) if use_graph else None
 
     def set_epoch(self, epoch):
         self.beta = kl_beta(epoch, self.hp.kl_warmup_epochs, self.hp.kl_warmup_smooth_start)
@@ -151,8 +157,13 @@ class Trainer:
             dist.all_reduce(self.state.G, op=dist.ReduceOp.SUM)
 
     def _advance_hyper(self):
-        """Host side of the optimizer step: count it, push a changed learning rate
-        (fill_ carries the value in the launch arguments: no pinned-buffer race)."""
+        """Host side of the optimizer step: count it, evaluate the learning-rate schedule
+        (per step, like the reference's Keras callback, util/learning_rate_schedule.py:55-79)
+        and push a changed value (fill_ carries it in the launch arguments: no pinned-buffer race)."""
+        hp = self.hp
+        if self.use_schedule and hp.learning_rate_schedule == "cosine_warmup":
+            self.lr = cosine_warmup_lr(self.step_count, self.steps_per_epoch, hp.learning_rate,
+                                       hp.lr_min_learning_rate, hp.lr_warmup_epochs, hp.lr_first_decay_epochs)
         self.step_count += 1
         if float(self.lr) != self._lr_pushed:
             self._lr_pushed = float(self.lr)
@@ -183,7 +194,7 @@ class Trainer:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=self._side):
             nll, kl = self._step_body(self._static["x"])
         self.graph_launches = _lib.launch_count() - before
         _lib.add_launches(-self.graph_launches)       # capture enqueued nothing; replays are counted below
@@ -195,8 +206,15 @@ class Trainer:
         per-image nll and kl tensors of the shard (device, no host sync)."""
         self._advance_hyper()
         graph_ok = self.use_graph and eps is None and noise is None
-        if not graph_ok or self.step_count <= self.graph_warmup:
+        if not graph_ok:
             return self._step_body(x, eps, noise)
+        if self.step_count <= self.graph_warmup:
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                out = self._step_body(x, eps, noise)
+            cur.wait_stream(self._side)
+            return out
         if self._graph is None:
             self._capture(x)
         self._static["x"].copy_(x, non_blocking=True)

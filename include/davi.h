@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DAVI_VERSION 100          /* major*100 + minor */
+#define DAVI_VERSION 101          /* major*100 + minor */
 #define DAVI_MAX_SLOTS 32         /* max stacked layers n of the depth-wise attention */
 
 #define DAVI_OK 0
@@ -140,26 +140,32 @@ int davi_ln_gelu_bwd(const float* x, const float* gamma, const float* beta,
  *     O = softmax_rows(scale * Q K^T) V,   y = gamma * O + x
  * Q,K [B,N,d] (row strides q_s,k_s), V [B,N,C] (v_s), x,y [B,N,C] (x_s,y_s);
  * batch strides are N*row_stride.  lse [B,N] dense: row log-sum-exp of the
- * scaled logits, saved for the backward.  d % 4 == 0, d <= 64, C % 4 == 0.
+ * scaled logits, saved for the backward.  o_save (nullable) [B,N,C] row stride
+ * o_s: a copy of O, which the tensor-core backward needs (E_i = <dy_i, O_i>).
+ * d % 4 == 0, C % 4 == 0.  N % 128 == 0, d <= 32, C <= 320 run on the tensor
+ * cores (tcgen05, 3xTF32 error-compensated = fp32-grade results); other shapes
+ * (N % 16 == 0, d <= 64, C <= 512) on an exact-fp32 CUDA-core kernel.
  * scale (nullable = 1.0) and gamma are DEVICE scalars: the trained weights
  * `scale` (layers/attention.py:84-92) and `gamma` (layers/attention.py:256-261).
  * ---------------------------------------------------------------------- */
 int davi_nonlocal_attn_fwd(const float* Q, const float* K, const float* V,
-                           const float* x, float* y, float* lse,
+                           const float* x, float* y, float* lse, float* o_save,
                            int B, int N, int d, int C,
                            int64_t q_s, int64_t k_s, int64_t v_s, int64_t x_s, int64_t y_s,
+                           int64_t o_s,
                            const float* scale, const float* gamma, davi_stream_t stream);
 
 /* Gradient: dy [B,N,C] -> dQ,dK,dV (same strides as
- * Q,K,V); dx == dy is left to the caller.  dgamma_dscale: TWO floats,
- * overwritten with { sum(O*dy), sum(dS * QK^T) }.
+ * Q,K,V); dx == dy is left to the caller.  O (nullable): the o_save copy of the
+ * forward; without it the CUDA-core kernels are used.  dgamma_dscale: TWO
+ * floats, overwritten with { sum(O*dy), sum(dS * QK^T) }.
  * workspace: davi_nonlocal_attn_bwd_workspace_bytes. */
 size_t davi_nonlocal_attn_bwd_workspace_bytes(int B, int N, int d, int C);
 int davi_nonlocal_attn_bwd(const float* Q, const float* K, const float* V,
-                           const float* lse, const float* dy,
+                           const float* lse, const float* O, const float* dy,
                            float* dQ, float* dK, float* dV, float* dgamma_dscale,
                            int B, int N, int d, int C,
-                           int64_t q_s, int64_t k_s, int64_t v_s, int64_t dy_s,
+                           int64_t q_s, int64_t k_s, int64_t v_s, int64_t o_s, int64_t dy_s,
                            const float* scale, const float* gamma,
                            void* workspace, size_t workspace_bytes, davi_stream_t stream);
 

@@ -44,7 +44,7 @@ def test_ctypes_table_matches_header(libdavi):
 
 
 def test_version_and_error_text(libdavi):
-    assert libdavi.davi_version() == 100
+    assert libdavi.davi_version() == 101
     rc = libdavi.davi_dw_attn_fwd(None, None, None, None, None, 1, 1, 1, 4, 4,
                                   4, 4, 4, 4, 4, 4, 4, 4, None, None)
     assert rc == -1  # DAVI_EINVAL, nothing launched
@@ -55,8 +55,8 @@ def test_version_and_error_text(libdavi):
 
 def test_validation_rejects_bad_shapes(libdavi):
     one = ctypes.c_void_p(16)  # aligned dummy, never dereferenced: validation comes first
-    rc = libdavi.davi_nonlocal_attn_fwd(one, one, one, one, one, one, 1, 250, 32, 64,
-                                        32, 32, 64, 64, 64, None, one, None)
+    rc = libdavi.davi_nonlocal_attn_fwd(one, one, one, one, one, one, None, 1, 250, 32, 64,
+                                        32, 32, 64, 64, 64, 64, None, one, None)
     assert rc == -1
     rc = libdavi.davi_dw_attn_fwd(one, one, one, one, None, 1, 33, 16, 20, 276,
                                   20, 1, 1, 20, 1, 1, 276, 276, None, None)

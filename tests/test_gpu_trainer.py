@@ -69,4 +69,5 @@ def test_graph_replay_equals_eager_step(cuda):
     assert s0 == s1 == 6.0
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 1e-4 * abs(a), (l0, l1)
-    assert (p0 - p1).abs().max().item() < 1e-4
+    # Adamax moves a weight by up to lr = 1e-2 per step: allow 10 % of ONE step after six
+    assert (p0 - p1).abs().max().item() < 1e-3

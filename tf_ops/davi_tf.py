@@ -34,10 +34,10 @@ def _dw_attn_grad(op, dout):
 
 
 @tf_ops.RegisterGradient("DaviNonlocalAttn")
-def _nonlocal_grad(op, dy, _dlse):
+def _nonlocal_grad(op, dy, _dlse, _do):
     q, k, v, x, scale, gamma = op.inputs
     dq, dk, dv, dgs = _mod.davi_nonlocal_attn_grad(q=q, k=k, v=v, lse=op.outputs[1], scale=scale,
-                                                   gamma=gamma, dy=dy)
+                                                   gamma=gamma, dy=dy, o=op.outputs[2])
     return dq, dk, dv, dy, dgs[1], dgs[0]          # d x == dy (residual)
 
 
@@ -71,7 +71,7 @@ def depthwise_attention_apply(self, query, keys, values):
 def nonlocal_core(q, k, v, x, scale, gamma):
     """softmax(scale q k^T) v * gamma + x for NonlocalResNetBlock.call (att.py:318-389);
     q,k,v are the outputs of the block's three 1x1 convolutions, NHWC."""
-    y, _ = _mod.davi_nonlocal_attn(q=q, k=k, v=v, x=x, scale=scale, gamma=gamma)
+    y, _, _ = _mod.davi_nonlocal_attn(q=q, k=k, v=v, x=x, scale=scale, gamma=gamma)
     return y
 
 

@@ -135,10 +135,11 @@ REGISTER_KERNEL_BUILDER(Name("DaviDwAttnGrad").Device(tf::DEVICE_GPU), DaviDwAtt
 REGISTER_OP("DaviNonlocalAttn")
     .Input("q: float").Input("k: float").Input("v: float").Input("x: float")
     .Input("scale: float").Input("gamma: float")
-    .Output("y: float").Output("lse: float")
+    .Output("y: float").Output("lse: float").Output("o: float")
     .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
       c->set_output(0, c->input(3));
       c->set_output(1, c->UnknownShapeOfRank(2));
+      c->set_output(2, c->input(3));
       return tf::Status::OK();
     });
 
@@ -149,11 +150,12 @@ class DaviNonlocalAttnOp : public OpKernel {
     const Tensor &q = ctx->input(0), &k = ctx->input(1), &v = ctx->input(2), &x = ctx->input(3);
     const int B = x.dim_size(0), N = x.dim_size(1) * x.dim_size(2);
     const int d = q.dim_size(3), C = x.dim_size(3);
-    Tensor *y, *lse;
+    Tensor *y, *lse, *o;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x.shape(), &y));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({B, N}), &lse));
-    OP_REQUIRES_OK(ctx, Check(davi_nonlocal_attn_fwd(P(q), P(k), P(v), P(x), P(y), P(lse), B, N, d, C,
-                                                     d, d, C, C, C, P(ctx->input(4)), P(ctx->input(5)),
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, x.shape(), &o));   // copy of O for the gradient op
+    OP_REQUIRES_OK(ctx, Check(davi_nonlocal_attn_fwd(P(q), P(k), P(v), P(x), P(y), P(lse), P(o), B, N, d, C,
+                                                     d, d, C, C, C, C, P(ctx->input(4)), P(ctx->input(5)),
                                                      StreamOf(ctx)),
                               "davi_nonlocal_attn_fwd"));
   }
@@ -162,7 +164,7 @@ REGISTER_KERNEL_BUILDER(Name("DaviNonlocalAttn").Device(tf::DEVICE_GPU), DaviNon
 
 REGISTER_OP("DaviNonlocalAttnGrad")
     .Input("q: float").Input("k: float").Input("v: float").Input("lse: float")
-    .Input("scale: float").Input("gamma: float").Input("dy: float")
+    .Input("scale: float").Input("gamma: float").Input("dy: float").Input("o: float")
     .Output("dq: float").Output("dk: float").Output("dv: float").Output("dgamma_dscale: float")
     .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
       for (int i = 0; i < 3; ++i) c->set_output(i, c->input(i));
@@ -175,7 +177,7 @@ class DaviNonlocalAttnGradOp : public OpKernel {
   explicit DaviNonlocalAttnGradOp(OpKernelConstruction* c) : OpKernel(c) {}
   void Compute(OpKernelContext* ctx) override {
     const Tensor &q = ctx->input(0), &k = ctx->input(1), &v = ctx->input(2), &lse = ctx->input(3);
-    const Tensor& dy = ctx->input(6);
+    const Tensor &dy = ctx->input(6), &o = ctx->input(7);
     const int B = v.dim_size(0), N = v.dim_size(1) * v.dim_size(2);
     const int d = q.dim_size(3), C = v.dim_size(3);
     Tensor *dq, *dk, *dv, *dgs, ws;
@@ -185,8 +187,8 @@ class DaviNonlocalAttnGradOp : public OpKernel {
     OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({2}), &dgs));
     const size_t wsb = davi_nonlocal_attn_bwd_workspace_bytes(B, N, d, C);
     OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, TensorShape({(tf::int64)((wsb + 3) / 4)}), &ws));
-    OP_REQUIRES_OK(ctx, Check(davi_nonlocal_attn_bwd(P(q), P(k), P(v), P(lse), P(dy), P(dq), P(dk), P(dv),
-                                                     P(dgs), B, N, d, C, d, d, C, C, P(ctx->input(4)),
+    OP_REQUIRES_OK(ctx, Check(davi_nonlocal_attn_bwd(P(q), P(k), P(v), P(lse), P(o), P(dy), P(dq), P(dk), P(dv),
+                                                     P(dgs), B, N, d, C, d, d, C, C, C, P(ctx->input(4)),
                                                      P(ctx->input(5)), P(&ws), wsb, StreamOf(ctx)),
                               "davi_nonlocal_attn_bwd"));
   }

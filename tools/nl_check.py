@@ -40,7 +40,12 @@ def case(B, HW, d, C, bwd, timing=True):
     if bwd:
         y.backward(go.to(dev))
         want.backward(go[:nb].double())
-        out["dqkv_err"] = rel(qkv_g.grad[:nb], qkv_r.grad)
+        out["dq_err"] = rel(qkv_g.grad[:nb, ..., :d], qkv_r.grad[..., :d])
+        out["dk_err"] = rel(qkv_g.grad[:nb, ..., d:2 * d], qkv_r.grad[..., d:2 * d])
+        out["dv_err"] = rel(qkv_g.grad[:nb, ..., 2 * d:], qkv_r.grad[..., 2 * d:])
+        if nb == B:
+            out["dgamma_err"] = abs(g_g.grad.item() - g_r.grad.item()) / max(abs(g_r.grad.item()), 1e-30)
+            out["dscale_err"] = abs(s_g.grad.item() - s_r.grad.item()) / max(abs(s_r.grad.item()), 1e-30)
     if timing:
         from deep_attentive_vi_b200 import _lib
         N = HW * HW
@@ -58,10 +63,12 @@ def case(B, HW, d, C, bwd, timing=True):
         qp, kp, vp = qd.data_ptr(), qd.data_ptr() + 4 * d, qd.data_ptr() + 8 * d
         dqp, dkp, dvp = dqkv.data_ptr(), dqkv.data_ptr() + 4 * d, dqkv.data_ptr() + 8 * d
         sp, gp = s_g.detach().data_ptr(), g_g.detach().data_ptr()
+        osave = torch.empty_like(xx)
         fwd = lambda: _lib.call("davi_nonlocal_attn_fwd", qp, kp, vp, xx.data_ptr(), yb.data_ptr(), lse.data_ptr(),
-                                B, N, d, C, rs, rs, rs, C, C, sp, gp, st)
-        bwdf = lambda: _lib.call("davi_nonlocal_attn_bwd", qp, kp, vp, lse.data_ptr(), god.data_ptr(), dqp, dkp, dvp,
-                                 dgs.data_ptr(), B, N, d, C, rs, rs, rs, C, sp, gp, ws.data_ptr(), wsb, st)
+                                osave.data_ptr(), B, N, d, C, rs, rs, rs, C, C, C, sp, gp, st)
+        bwdf = lambda: _lib.call("davi_nonlocal_attn_bwd", qp, kp, vp, lse.data_ptr(), osave.data_ptr(),
+                                 god.data_ptr(), dqp, dkp, dvp, dgs.data_ptr(), B, N, d, C, rs, rs, rs, C, C, sp, gp,
+                                 ws.data_ptr(), wsb, st)
 
         def timeit(fn):
             ts = []
