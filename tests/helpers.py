@@ -79,3 +79,85 @@ def synthetic_images(kw, batch, seed=0):
         p = info["pad_size"]
         return torch.nn.functional.pad(x, (0, 0, p, p, p, p))
     return torch.randint(0, 256, (batch, h, w, c), generator=g).float()
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures produced by the reference's own code (tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------
+import os as _os
+import re as _re
+
+GOLDEN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+_LN_NAMES = {"_cond_attention_layer_norm_layer": "cond_ln", "_encoder_attention_layer_norm_layer": "enc_ln",
+             "_attention_layer_norm_layer": "attn_ln", "_attention_layer_norm_layer2": "attn_ln2",
+             "_ctx_layer_norm_layer": "ctx_ln"}
+
+
+def reference_key_to_host(path, name):
+    """Attribute path + variable name of the reference (Keras) model -> (host state_dict key, is_conv_kernel)."""
+    path = _re.sub(r"_shortcut\.conv_(\d)", lambda m: f"_shortcut.convs.{int(m.group(1)) - 1}", path)
+    path = path.replace(".layers.1.", ".")        # Sequential([Lambda(resize), Conv2D]) of up-sampling blocks
+    leaf = path.rsplit(".", 1)[-1]
+    if path.endswith(".layer"):                                   # the wrapped Keras Conv2D of a WeightNorm
+        base = path[:-len(".layer")]
+        return (f"{base}.v", True) if name == "kernel" else (f"{base}.bias", False)
+    if name == "g":
+        return f"{path}.log_g", False
+    if leaf == "_batch_norm_layer":
+        return f"{path}.bn." + {"gamma": "weight", "beta": "bias", "moving_mean": "running_mean",
+                                "moving_variance": "running_var"}[name], False
+    if leaf in _LN_NAMES:
+        return f"{path.rsplit('.', 1)[0]}.{_LN_NAMES[leaf]}_{name}", False
+    if _re.fullmatch(r"_ctx_layer_norm\.\d+", path):
+        return f"{path}.{0 if name == 'gamma' else 1}", False
+    if _re.fullmatch(r"_latent_layer\.\d+", path):
+        return f"{path}." + {"gamma": "_gamma", "enc_gamma": "_encoder_gamma"}[name], False
+    if leaf == "_decoder_network" and name == "constant":
+        return f"{path.rsplit('.', 1)[0]}._decoder_const", False
+    return f"{path}.{name}", False                                # nonlocal gamma, alignment scale ...
+
+
+def load_reference_golden(fname, model):
+    """Loads tests/golden/<fname>: returns (fixture dict, host state_dict built from the reference's
+    weights).  Every floating-point entry of the host model must be covered."""
+    import numpy as np
+    z = np.load(_os.path.join(GOLDEN_DIR, fname))
+    want = {k: v for k, v in model.state_dict().items()}
+    sd = {}
+    for key in z.files:
+        if not key.startswith("w/"):
+            continue
+        _, path, name = key.split("/")
+        hk, is_kernel = reference_key_to_host(path, name)
+        w = torch.from_numpy(z[key])
+        if is_kernel:
+            w = w.permute(3, 2, 0, 1).contiguous()                # TF [kh,kw,in,out] -> torch [out,in,kh,kw]
+        assert hk in want, f"reference weight {path}/{name} -> {hk} has no counterpart in the host model"
+        assert tuple(want[hk].shape) == tuple(w.shape), (hk, tuple(want[hk].shape), tuple(w.shape))
+        sd[hk] = w
+    missing = [k for k, v in want.items() if k not in sd and v.is_floating_point()]
+    assert not missing, f"host parameters without a reference weight: {missing[:8]}"
+    for k, v in want.items():
+        sd.setdefault(k, v)
+    return {k: z[k] for k in z.files if not k.startswith("w/")}, sd
+
+
+def golden_noise(fix, mode, L, training_noise):
+    """The recorded normal draws in call order -> (eps list, noise list) of DeepVAE.forward:
+    layer 0 draws [posterior noise], eps; layer i > 0 draws [prior noise, posterior noise], eps
+    (vl.py:463 before vl.py:511)."""
+    draws = [(k.rsplit("/", 1)[-1], torch.from_numpy(fix[k])) for k in sorted(fix) if k.startswith(f"{mode}/draw/")]
+    it = iter(draws)
+    eps, noise = [], []
+    for i in range(L):
+        pn = qn = None
+        if training_noise:
+            if i > 0:
+                tag, pn = next(it); assert tag == "gaussian_noise"
+            tag, qn = next(it); assert tag == "gaussian_noise"
+        tag, e = next(it); assert tag == "mvn_sample"
+        eps.append(e[0])
+        noise.append((qn, pn))
+    assert next(it, None) is None
+    return eps, (noise if training_noise else None)

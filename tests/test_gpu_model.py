@@ -67,3 +67,33 @@ def test_importance_sampled_chunk_matches_oracle(cuda):
     with torch.no_grad():
         got = m.infer_worker_body(x.to(cuda), S, eps=[e.to(cuda) for e in eps])
     assert ((got.double().cpu() - want).abs() / want.abs()).max() < 1e-4
+
+
+@pytest.mark.parametrize("flags,fname", [(helpers.SMALL_CIFAR, "ref_small_cifar.npz"),
+                                         (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz")], ids=["cifar", "omniglot"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_elbo_matches_reference_code_golden(cuda, flags, fname, mode):
+    """The CUDA path against the committed output of the reference's OWN DeepVAE.call (executed in
+    float64 through tests/golden/tf_shim.py) on the reference's weights, images and random draws.
+    Bar: 1e-4 relative on nll, sum(kl) and nelbo (fp32 kernels, fp32 cuDNN convs)."""
+    import numpy as np
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    _fp32_exact()
+    kw = parse_flags(**flags)
+    m = DeepVAE(**kw)
+    fix, sd = helpers.load_reference_golden(fname, m)
+    m.load_state_dict(sd)
+    training = mode == "train"
+    has_noise = training and kw["posterior_hparams"].noise_stddev > 0
+    eps, noise = helpers.golden_noise(fix, mode, kw["hparams"].num_layers, has_noise)
+    m = m.to(cuda)
+    if not training:
+        m.eval()
+    dev = lambda t: None if t is None else t.float().to(cuda)
+    with torch.no_grad():
+        out = m(torch.from_numpy(fix["x"]).float().to(cuda), training, [dev(e) for e in eps],
+                None if noise is None else [(dev(a), dev(b)) for a, b in noise])
+    for got, name in zip(out, ("nll", "kl", "nelbo")):
+        want = torch.from_numpy(np.asarray(fix[f"{mode}/{name}"]))
+        rel = ((got.double().cpu() - want).abs() / want.abs()).max().item()
+        assert rel < 1e-4, (name, rel)
