@@ -321,7 +321,13 @@ def run_davi(args):
                                               "(oracle/, torch CPU fp32, all host threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: a captured CUDA graph holds NCCL kernels, and destroy_process_group() with such a
+        # graph alive can block forever.  Synchronise, then leave without running the destructors.
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
