@@ -16,6 +16,7 @@ _r = ctypes.c_float
 _s = ctypes.c_void_p      # cudaStream_t
 _z = ctypes.c_size_t
 _pp = ctypes.POINTER(ctypes.c_void_p)
+_lp = ctypes.POINTER(ctypes.c_int64)
 
 # name -> (restype, argtypes); mirrors include/davi.h declaration by declaration
 SIGNATURES = {
@@ -23,8 +24,9 @@ SIGNATURES = {
     "davi_last_error": (_i, [ctypes.c_char_p, _z]),
     "davi_dw_attn_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _l, _l, _f, _s]),
     "davi_dw_attn_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _l, _l, _f, _s]),
-    "davi_dw_attn_slots_fwd": (_i, [_f, _pp, _pp, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _f, _s]),
-    "davi_dw_attn_slots_bwd": (_i, [_f, _pp, _pp, _f, _f, _pp, _pp, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _f, _i, _s]),
+    "davi_dw_attn_slots_fwd": (_i, [_f, _pp, _pp, _lp, _lp, _f, _f, _i, _i, _i, _i, _i, _l, _l, _f, _s]),
+    "davi_dw_attn_slots_bwd": (_i, [_f, _pp, _pp, _lp, _lp, _f, _f, _pp, _pp, _lp, _lp, _f, _i, _i, _i, _i, _i,
+                                    _l, _l, _f, ctypes.c_uint32, _s]),
     "davi_ln_gelu_fwd": (_i, [_f, _f, _f, _f, _l, _i, _l, _l, _r, _i, _s]),
     "davi_ln_gelu_bwd_workspace_bytes": (_z, [_l, _i]),
     "davi_ln_gelu_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _l, _i, _l, _l, _l, _r, _i, _f, _z, _s]),
@@ -37,6 +39,8 @@ SIGNATURES = {
     "davi_bernoulli_nll_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _s]),
     "davi_scale_rows": (_i, [_f, _f, _f, _i, _l, _s]),
     "davi_is_logsumexp": (_i, [_f, _f, _i, _i, _s]),
+    "davi_weight_norm_fwd": (_i, [_f, _f, _f, _f, _f, _f, _l, _s]),
+    "davi_weight_norm_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _l, _s]),
     "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
     "davi_adamax_step_dev": (_i, [_f, _f, _f, _f, _l, _f, _r, _r, _r, _r, _s]),
 }
@@ -105,3 +109,9 @@ def ptr_table(ptrs):
     """Host array of device pointers for the *_slots_* entry points."""
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     return ctypes.cast(arr, _pp), arr  # keep `arr` alive for the duration of the call
+
+
+def int_table(vals):
+    """Host array of int64 (per-slot strides)."""
+    arr = (ctypes.c_int64 * len(vals))(*vals)
+    return ctypes.cast(arr, _lp), arr

@@ -16,23 +16,41 @@
 //     of the reference never exist.
 // Algorithmic bytes: fwd 4*B*P*(n*(d+C)+d+C), bwd
 // 4*B*P*(2n(d+C)+2d+C); the kernels touch each of those bytes once.
+#include <stdlib.h>
+#include <string.h>
+
 #include "davi_common.cuh"
 
 namespace davi {
 
+// every slot carries its own (batch, pixel) strides: a slot may be a channel slice of a wider
+// per-layer tensor, a dense fresh tensor, or layer j of a stacked tensor
 struct SlotPtrs {
     const float* k[DAVI_MAX_SLOTS];
     const float* v[DAVI_MAX_SLOTS];
+    int k_sb[DAVI_MAX_SLOTS], k_sp[DAVI_MAX_SLOTS];
+    int v_sb[DAVI_MAX_SLOTS], v_sp[DAVI_MAX_SLOTS];
 };
 struct SlotGradPtrs {
     float* dk[DAVI_MAX_SLOTS];
     float* dv[DAVI_MAX_SLOTS];
+    int k_sb[DAVI_MAX_SLOTS], k_sp[DAVI_MAX_SLOTS];
+    int v_sb[DAVI_MAX_SLOTS], v_sp[DAVI_MAX_SLOTS];
 };
 
 struct DwGeom {
     int n, P, total_pix, d4, C4;
-    int64_t q_sp, k_sb, k_sp, v_sb, v_sp, o_sp;
+    int64_t q_sp, o_sp;
+    uint32_t acc_mask;       // backward: bit j set = slot j's dK/dV are accumulated (+=), else overwritten
     const float* scale_ptr;  // device scalar, nullptr = 1.0
+};
+
+// per-CTA copy of the slot table with the pixel offsets of THIS thread's pixel resolved lazily
+struct SlotTable {
+    const float* k[DAVI_MAX_SLOTS];
+    const float* v[DAVI_MAX_SLOTS];
+    int k_sb[DAVI_MAX_SLOTS], k_sp[DAVI_MAX_SLOTS];
+    int v_sb[DAVI_MAX_SLOTS], v_sp[DAVI_MAX_SLOTS];
 };
 
 constexpr int kDwThreads = 128;
@@ -41,8 +59,8 @@ constexpr int kDwUnroll = 4;  // slots whose value rows are in flight together
 // softmax over the n slots of one pixel; lane l of the group holds slots l+t*G.
 // returns a[t] (weights) and, if R != nullptr, the raw dot products r[t].
 template <int G, int SPL>
-__device__ __forceinline__ void dw_scores(const float* const* s_k, const DwGeom& g, int l,
-                                          int64_t koff, const float* qp, float (&a)[SPL],
+__device__ __forceinline__ void dw_scores(const SlotTable& tb, const DwGeom& g, int l,
+                                          int b, int p, const float* qp, float (&a)[SPL],
                                           float* r_raw, unsigned gm, float scale) {
     float s[SPL];
     float m = -INFINITY;
@@ -51,7 +69,7 @@ __device__ __forceinline__ void dw_scores(const float* const* s_k, const DwGeom&
         const int j = l + t * G;
         s[t] = -INFINITY;
         if (j < g.n) {
-            const float* kp = s_k[j] + koff;
+            const float* kp = tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j];
             float dot = 0.f;
             for (int c = 0; c < g.d4; ++c) dot += dot4(ld4(kp + 4 * c), ld4(qp + 4 * c));
             if (r_raw) r_raw[t] = dot;
@@ -79,11 +97,12 @@ __global__ void __launch_bounds__(kDwThreads)
 dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __restrict__ out,
                    float* __restrict__ attn, const DwGeom g) {
     constexpr int SPL = DAVI_MAX_SLOTS / G;
-    __shared__ const float* s_k[DAVI_MAX_SLOTS];
-    __shared__ const float* s_v[DAVI_MAX_SLOTS];
+    __shared__ SlotTable tb;
     if (threadIdx.x < DAVI_MAX_SLOTS) {
-        s_k[threadIdx.x] = sp.k[threadIdx.x];
-        s_v[threadIdx.x] = sp.v[threadIdx.x];
+        const int j = threadIdx.x;
+        tb.k[j] = sp.k[j]; tb.v[j] = sp.v[j];
+        tb.k_sb[j] = sp.k_sb[j]; tb.k_sp[j] = sp.k_sp[j];
+        tb.v_sb[j] = sp.v_sb[j]; tb.v_sp[j] = sp.v_sp[j];
     }
     __syncthreads();
 
@@ -92,14 +111,13 @@ dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __rest
     const int pix = (blockIdx.x * kDwThreads + threadIdx.x) / G;
     if (pix >= g.total_pix) return;  // whole groups exit together (G divides 32)
     const int b = pix / g.P, p = pix - b * g.P;
-    const int64_t koff = (int64_t)b * g.k_sb + (int64_t)p * g.k_sp;
-    const int64_t voff = (int64_t)b * g.v_sb + (int64_t)p * g.v_sp;
+    auto vrow = [&](int j) { return tb.v[j] + (int64_t)b * tb.v_sb[j] + (int64_t)p * tb.v_sp[j] + 4 * l; };
     const float* qp = q + (int64_t)pix * g.q_sp;
 
     float a[SPL];
     const unsigned gm = group_mask<G>();
     const float scale = g.scale_ptr ? __ldg(g.scale_ptr) : 1.f;
-    dw_scores<G, SPL>(s_k, g, l, koff, qp, a, nullptr, gm, scale);
+    dw_scores<G, SPL>(tb, g, l, b, p, qp, a, nullptr, gm, scale);
     if (attn) {
 #pragma unroll
         for (int t = 0; t < SPL; ++t)
@@ -119,7 +137,7 @@ dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __rest
             float4 v[kDwUnroll][ITERS];
 #pragma unroll
             for (int u = 0; u < kDwUnroll; ++u) {
-                const float* vp = s_v[j + u] + voff + 4 * l;
+                const float* vp = vrow(j + u);
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
                     if (it < ITERS - 1 || last_ok) v[u][it] = ld_stream4(vp + 4 * it * G);
@@ -134,7 +152,7 @@ dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __rest
             }
         }
         for (; j < jend; ++j) {
-            const float* vp = s_v[j] + voff + 4 * l;
+            const float* vp = vrow(j);
             float4 v[ITERS];
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
@@ -153,25 +171,195 @@ dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __rest
         if (it < ITERS - 1 || last_ok) st_stream4(op + 4 * it * G, acc[it]);
 }
 
+// ---------------------------------------------------------------------------------------
+// Forward, version 2: persistent, bulk-copy staged.  The register-streaming kernel above tops
+// out near 5 TB/s (ncu: profiles/r01_ncu_dw_attn_v1_summary.txt -- 25 % occupancy, every warp
+// stalled on its own loads, and a third partial wave).  Here one CTA per SM walks tiles of 8
+// pixels; ONE thread feeds a 16-stage shared-memory ring with cp.async.bulk copies of whole
+// value tiles (8 rows, ~9 KB, contiguous in HBM), four "score" warps compute the softmax
+// weights of the NEXT tile from q and the key rows while four "stream" warps multiply-accumulate
+// the staged value tiles of the current one.  ~150 KB per SM are in flight independently of
+// register pressure, DRAM sees multi-KB sequential bursts, and there is no wave tail.
+// ---------------------------------------------------------------------------------------
+constexpr int kV2TP = 8;                  // pixels per tile
+constexpr int kV2Stages = 16;
+constexpr int kV2Threads = 288;           // warp 0: producer | warps 1-4: scores | warps 5-8: stream
+constexpr int kV2Slack = 32;              // floats of row padding a single-span copy may carry along
+
+struct V2Bars {
+    uint64_t v_full[kV2Stages], v_empty[kV2Stages];
+    uint64_t a_full[2], a_empty[2];
+};
+
+__device__ __forceinline__ uint32_t v2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void v2_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(v2_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(v2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void v2_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(v2_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void v2_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(v2_smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();      // never hang the GPU: fail the launch instead
+    }
+}
+__device__ __forceinline__ void v2_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            v2_smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(v2_smem_u32(bar))
+        : "memory");
+}
+
+// per-slot staging plan: a tile of slot j is either one contiguous span (row stride kept) or,
+// when the slot's rows are far apart, kV2TP row copies packed densely
+__device__ __forceinline__ bool v2_single_span(int v_sp, int C) { return v_sp - C <= kV2Slack; }
+
+template <int ITERS>
+__global__ void __launch_bounds__(kV2Threads, 1)
+dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __restrict__ out,
+                      float* __restrict__ attn, const DwGeom g, const int ntiles) {
+    constexpr int G = 16, SPL = DAVI_MAX_SLOTS / G;
+    extern __shared__ __align__(128) uint8_t v2_smem[];
+    __shared__ SlotTable tb;
+    __shared__ V2Bars bars;
+    __shared__ float s_a[2][kV2TP][DAVI_MAX_SLOTS];
+    const int C = g.C4 * 4;
+    const int stage_floats = kV2TP * (C + kV2Slack);
+    float* ring = reinterpret_cast<float*>(v2_smem);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid < DAVI_MAX_SLOTS) {
+        const int j = tid;
+        tb.k[j] = sp.k[j]; tb.v[j] = sp.v[j];
+        tb.k_sb[j] = sp.k_sb[j]; tb.k_sp[j] = sp.k_sp[j];
+        tb.v_sb[j] = sp.v_sb[j]; tb.v_sp[j] = sp.v_sp[j];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kV2Stages; ++s) { v2_mbar_init(&bars.v_full[s], 1); v2_mbar_init(&bars.v_empty[s], 128); }
+        for (int i = 0; i < 2; ++i) { v2_mbar_init(&bars.a_full[i], 128); v2_mbar_init(&bars.a_empty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer: one thread issues every bulk copy ----------------
+        if (tid == 0) {
+            uint32_t gc = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int pix0 = t * kV2TP;
+                const int b = pix0 / g.P, p0 = pix0 - b * g.P;
+                for (int j = 0; j < g.n; ++j, ++gc) {
+                    const int s = gc % kV2Stages;
+                    if (gc >= kV2Stages) v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1);
+                    const int vsp = tb.v_sp[j];
+                    const float* src = tb.v[j] + (int64_t)b * tb.v_sb[j] + (int64_t)p0 * vsp;
+                    float* dst = ring + (size_t)s * stage_floats;
+                    if (v2_single_span(vsp, C)) {
+                        const uint32_t bytes = (uint32_t)((kV2TP - 1) * vsp + C) * 4u;
+                        v2_mbar_expect_tx(&bars.v_full[s], bytes);
+                        v2_bulk_load(dst, src, bytes, &bars.v_full[s]);
+                    } else {
+                        v2_mbar_expect_tx(&bars.v_full[s], (uint32_t)(kV2TP * C) * 4u);
+                        for (int r = 0; r < kV2TP; ++r)
+                            v2_bulk_load(dst + r * C, src + (int64_t)r * vsp, (uint32_t)C * 4u, &bars.v_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp <= 4) {
+        // ---------------- score warps: softmax weights of each tile -> s_a ----------------
+        const int lt = tid - 32;
+        const int pixel = lt >> 4, l = lt & 15;
+        const unsigned gm = group_mask<G>();
+        const float scale = g.scale_ptr ? __ldg(g.scale_ptr) : 1.f;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int pix = t * kV2TP + pixel;
+            const int b = pix / g.P, p = pix - b * g.P;
+            float a[SPL];
+            dw_scores<G, SPL>(tb, g, l, b, p, q + (int64_t)pix * g.q_sp, a, nullptr, gm, scale);
+            const int buf = it & 1;
+            if (it >= 2) v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1);
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                const int j = l + u * G;
+                if (j < g.n) {
+                    s_a[buf][pixel][j] = a[u];
+                    if (attn) attn[(int64_t)pix * g.n + j] = a[u];
+                }
+            }
+            v2_mbar_arrive(&bars.a_full[buf]);          // arrive has release semantics for the stores above
+        }
+    } else {
+        // ---------------- stream warps: out = sum_j a_j * V_j over the staged tiles ----------------
+        const int lt = tid - 160;
+        const int pixel = lt >> 4, l = lt & 15;
+        const bool last_ok = (l + (ITERS - 1) * G) < g.C4;
+        uint32_t gc = 0, it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1);
+            float4 acc[ITERS];
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < g.n; ++j, ++gc) {
+                const int s = gc % kV2Stages;
+                const int vsp = tb.v_sp[j];
+                const int rs = v2_single_span(vsp, C) ? vsp : C;
+                const float aj = s_a[buf][pixel][j];
+                v2_mbar_wait(&bars.v_full[s], (gc / kV2Stages) & 1);
+                const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * l;
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i)
+                    if (i < ITERS - 1 || last_ok) fma4(acc[i], aj, *reinterpret_cast<const float4*>(row + 4 * i * G));
+                v2_mbar_arrive(&bars.v_empty[s]);
+            }
+            v2_mbar_arrive(&bars.a_empty[buf]);
+            float* op = out + (int64_t)(t * kV2TP + pixel) * g.o_sp + 4 * l;
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+                if (i < ITERS - 1 || last_ok) st_stream4(op + 4 * i * G, acc[i]);
+        }
+    }
+}
+
 // Backward.  Per pixel: recompute a; pass 1 streams V once for da_j = <V_j, g>;
 // ds_j = a_j (da_j - sum_k a_k da_k); pass 2 only writes: dV_j = a_j g,
 // dK_j = scale ds_j q, dq = scale sum_j ds_j K_j (K rows re-read from L1/L2).
-template <int G, int ITERS, bool ACC>
+template <int G, int ITERS>
 __global__ void __launch_bounds__(kDwThreads)
 dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __restrict__ q,
                    const float* __restrict__ dout, float* __restrict__ dq,
                    float* __restrict__ dscale, const DwGeom g) {
     constexpr int SPL = DAVI_MAX_SLOTS / G;
-    __shared__ const float* s_k[DAVI_MAX_SLOTS];
-    __shared__ const float* s_v[DAVI_MAX_SLOTS];
-    __shared__ float* s_dk[DAVI_MAX_SLOTS];
-    __shared__ float* s_dv[DAVI_MAX_SLOTS];
+    __shared__ SlotTable tb;
+    __shared__ SlotGradPtrs tg;
     __shared__ float red[32];
     if (threadIdx.x < DAVI_MAX_SLOTS) {
-        s_k[threadIdx.x] = sp.k[threadIdx.x];
-        s_v[threadIdx.x] = sp.v[threadIdx.x];
-        s_dk[threadIdx.x] = gp.dk[threadIdx.x];
-        s_dv[threadIdx.x] = gp.dv[threadIdx.x];
+        const int j = threadIdx.x;
+        tb.k[j] = sp.k[j]; tb.v[j] = sp.v[j];
+        tb.k_sb[j] = sp.k_sb[j]; tb.k_sp[j] = sp.k_sp[j];
+        tb.v_sb[j] = sp.v_sb[j]; tb.v_sp[j] = sp.v_sp[j];
+        tg.dk[j] = gp.dk[j]; tg.dv[j] = gp.dv[j];
+        tg.k_sb[j] = gp.k_sb[j]; tg.k_sp[j] = gp.k_sp[j];
+        tg.v_sb[j] = gp.v_sb[j]; tg.v_sp[j] = gp.v_sp[j];
     }
     __syncthreads();
 
@@ -183,14 +371,13 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
 
     if (active) {
         const int b = pix / g.P, p = pix - b * g.P;
-        const int64_t koff = (int64_t)b * g.k_sb + (int64_t)p * g.k_sp;
-        const int64_t voff = (int64_t)b * g.v_sb + (int64_t)p * g.v_sp;
+        auto vrow = [&](int j) { return tb.v[j] + (int64_t)b * tb.v_sb[j] + (int64_t)p * tb.v_sp[j] + 4 * l; };
         const float* qp = q + (int64_t)pix * g.q_sp;
 
         float a[SPL], r[SPL], da[SPL];
         const unsigned gm = group_mask<G>();
         const float scale = g.scale_ptr ? __ldg(g.scale_ptr) : 1.f;
-        dw_scores<G, SPL>(s_k, g, l, koff, qp, a, r, gm, scale);
+        dw_scores<G, SPL>(tb, g, l, b, p, qp, a, r, gm, scale);
 
         const bool last_ok = (l + (ITERS - 1) * G) < g.C4;
         float4 go[ITERS];
@@ -213,7 +400,7 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
                 float4 v[kDwUnroll][ITERS];
 #pragma unroll
                 for (int u = 0; u < kDwUnroll; ++u) {
-                    const float* vp = s_v[j + u] + voff + 4 * l;
+                    const float* vp = vrow(j + u);
 #pragma unroll
                     for (int it = 0; it < ITERS; ++it) {
                         if (it < ITERS - 1 || last_ok) v[u][it] = ld_stream4(vp + 4 * it * G);
@@ -230,7 +417,7 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
                 }
             }
             for (; j < jend; ++j) {
-                const float* vp = s_v[j] + voff + 4 * l;
+                const float* vp = vrow(j);
                 float part = 0.f;
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it)
@@ -262,14 +449,15 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
                 const int src = gbase + (j & (G - 1));
                 const float aj = __shfl_sync(gm, a[t], src);
                 const float dsj = __shfl_sync(gm, ds[t], src) * scale;
-                float* dvp = s_dv[j];
+                const bool acc = (g.acc_mask >> j) & 1u;
+                float* dvp = tg.dv[j];
                 if (dvp) {
-                    dvp += voff + 4 * l;
+                    dvp += (int64_t)b * tg.v_sb[j] + (int64_t)p * tg.v_sp[j] + 4 * l;
 #pragma unroll
                     for (int it = 0; it < ITERS; ++it) {
                         if (it < ITERS - 1 || last_ok) {
                             float4 o;
-                            if (ACC) {
+                            if (acc) {
                                 o = *reinterpret_cast<const float4*>(dvp + 4 * it * G);
                                 fma4(o, aj, go[it]);
                             } else {
@@ -281,13 +469,13 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
                     }
                 }
                 if (kcol) {
-                    const float4 kv = ld4(s_k[j] + koff + 4 * l);
+                    const float4 kv = ld4(tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j] + 4 * l);
                     fma4(dqv, dsj, kv);
-                    float* dkp = s_dk[j];
+                    float* dkp = tg.dk[j];
                     if (dkp) {
-                        dkp += koff + 4 * l;
+                        dkp += (int64_t)b * tg.k_sb[j] + (int64_t)p * tg.k_sp[j] + 4 * l;
                         float4 o;
-                        if (ACC) {
+                        if (acc) {
                             o = *reinterpret_cast<const float4*>(dkp);
                             fma4(o, dsj, qv);
                         } else {
@@ -318,9 +506,8 @@ static int dw_validate(const char* fn, int B, int n, int P, int d, int C, const 
         set_error("%s: need d %% 4 == 0 (<=128) and C %% 4 == 0 (<=512) (got d=%d C=%d)", fn, d, C);
         return DAVI_EINVAL;
     }
-    if (!mult4(g.q_sp) || !mult4(g.k_sb) || !mult4(g.k_sp) || !mult4(g.v_sb) || !mult4(g.v_sp) ||
-        !mult4(g.o_sp) || g.q_sp < d || g.k_sp < d || g.v_sp < C || g.o_sp < C) {
-        set_error("%s: strides must be multiples of 4 floats and >= the row width", fn);
+    if (!mult4(g.q_sp) || !mult4(g.o_sp) || g.q_sp < d || g.o_sp < C) {
+        set_error("%s: q/out strides must be multiples of 4 floats and >= the row width", fn);
         return DAVI_EINVAL;
     }
     if ((int64_t)B * P > 0x7fffffff / 32) {
@@ -328,6 +515,13 @@ static int dw_validate(const char* fn, int B, int n, int P, int d, int C, const 
         return DAVI_EINVAL;
     }
     return DAVI_OK;
+}
+
+// one slot's strides -> the int fields of the launch structs (validated)
+static bool put_strides(int64_t sb, int64_t sp, int width, int* o_sb, int* o_sp) {
+    if (!mult4(sb) || !mult4(sp) || sp < width || sb < 0 || sb > 0x7fffffff || sp > 0x7fffffff) return false;
+    *o_sb = (int)sb; *o_sp = (int)sp;
+    return true;
 }
 
 template <int G, int ITERS>
@@ -339,13 +533,10 @@ static void launch_fwd(const SlotPtrs& sp, const float* q, float* out, float* at
 }
 template <int G, int ITERS>
 static void launch_bwd(const SlotPtrs& sp, const SlotGradPtrs& gp, const float* q, const float* dout,
-                       float* dq, float* dscale, const DwGeom& g, bool acc, cudaStream_t st) {
+                       float* dq, float* dscale, const DwGeom& g, cudaStream_t st) {
     const int64_t threads = (int64_t)g.total_pix * G;
     const int grid = (int)((threads + kDwThreads - 1) / kDwThreads);
-    if (acc)
-        dw_attn_bwd_kernel<G, ITERS, true><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
-    else
-        dw_attn_bwd_kernel<G, ITERS, false><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
+    dw_attn_bwd_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
 }
 
 #define DW_DISPATCH(LAUNCH, ...)                                   \
@@ -369,6 +560,16 @@ static void launch_bwd(const SlotPtrs& sp, const SlotGradPtrs& gp, const float* 
         }                                                          \
     } while (0)
 
+// DAVI_DW_IMPL=v1 selects the register-streaming kernels (read once per process)
+static bool dw_v2_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DAVI_DW_IMPL");
+        v = (e && strcmp(e, "v1") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static int dw_fwd_impl(const char* fn, const SlotPtrs& sp, const float* q, float* out, float* attn,
                        int B, int n, int P, int d, int C, DwGeom g, cudaStream_t st) {
     g.n = n; g.P = P; g.total_pix = B * P; g.d4 = d / 4; g.C4 = C / 4;
@@ -383,13 +584,32 @@ static int dw_fwd_impl(const char* fn, const SlotPtrs& sp, const float* q, float
             set_error("%s: slot %d key/value pointer null or not 16-byte aligned", fn, j);
             return DAVI_EINVAL;
         }
+    if (dw_v2_enabled() && g.C4 > 32 && g.C4 <= 128 && P % kV2TP == 0) {
+        int dev = 0, sms = 0;
+        DAVI_CUDA(cudaGetDevice(&dev));
+        DAVI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int ntiles = g.total_pix / kV2TP;
+        const int grid = ntiles < sms ? ntiles : sms;
+        const size_t smem = (size_t)kV2Stages * kV2TP * (C + kV2Slack) * sizeof(float);
+        switch ((g.C4 + 15) / 16) {
+#define V2_CASE(I)                                                                                         \
+    case I:                                                                                                \
+        DAVI_CUDA(cudaFuncSetAttribute(dw_attn_fwd_v2_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                        \
+        dw_attn_fwd_v2_kernel<I><<<grid, kV2Threads, smem, st>>>(sp, q, out, attn, g, ntiles);             \
+        break;
+            V2_CASE(3) V2_CASE(4) V2_CASE(5) V2_CASE(6) V2_CASE(7) V2_CASE(8)
+#undef V2_CASE
+        }
+        return check_launch(fn);
+    }
     DW_DISPATCH(launch_fwd, sp, q, out, attn, g, st);
     return check_launch(fn);
 }
 
 static int dw_bwd_impl(const char* fn, const SlotPtrs& sp, const SlotGradPtrs& gp, const float* q,
                        const float* dout, float* dq, float* dscale, int B, int n, int P, int d, int C,
-                       DwGeom g, bool acc, cudaStream_t st) {
+                       DwGeom g, cudaStream_t st) {
     g.n = n; g.P = P; g.total_pix = B * P; g.d4 = d / 4; g.C4 = C / 4;
     int rc = dw_validate(fn, B, n, P, d, C, g);
     if (rc) return rc;
@@ -405,7 +625,7 @@ static int dw_bwd_impl(const char* fn, const SlotPtrs& sp, const SlotGradPtrs& g
         }
     }
     if (dscale) DAVI_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
-    DW_DISPATCH(launch_bwd, sp, gp, q, dout, dq, dscale, g, acc, st);
+    DW_DISPATCH(launch_bwd, sp, gp, q, dout, dq, dscale, g, st);
     return check_launch(fn);
 }
 
@@ -421,9 +641,12 @@ extern "C" int davi_dw_attn_fwd(const float* q, const float* keys, const float* 
     DAVI_REQUIRE(n >= 1 && n <= DAVI_MAX_SLOTS, "n out of range");
     DAVI_REQUIRE(mult4(k_sn) && mult4(v_sn), "layer strides must be multiples of 4");
     SlotPtrs sp{};
-    for (int j = 0; j < n; ++j) { sp.k[j] = keys + j * k_sn; sp.v[j] = values + j * v_sn; }
-    DwGeom g{}; g.q_sp = q_sp; g.k_sb = k_sb; g.k_sp = k_sp; g.v_sb = v_sb; g.v_sp = v_sp; g.o_sp = o_sp;
-    g.scale_ptr = scale;
+    for (int j = 0; j < n; ++j) {
+        sp.k[j] = keys + j * k_sn; sp.v[j] = values + j * v_sn;
+        DAVI_REQUIRE(put_strides(k_sb, k_sp, d, &sp.k_sb[j], &sp.k_sp[j]) &&
+                     put_strides(v_sb, v_sp, C, &sp.v_sb[j], &sp.v_sp[j]), "bad key/value strides");
+    }
+    DwGeom g{}; g.q_sp = q_sp; g.o_sp = o_sp; g.scale_ptr = scale;
     return dw_fwd_impl(__func__, sp, q, out, attn, B, n, P, d, C, g, (cudaStream_t)stream);
 }
 
@@ -440,42 +663,48 @@ extern "C" int davi_dw_attn_bwd(const float* q, const float* keys, const float* 
         sp.k[j] = keys + j * k_sn; sp.v[j] = values + j * v_sn;
         gp.dk[j] = dkeys ? dkeys + j * k_sn : nullptr;
         gp.dv[j] = dvalues ? dvalues + j * v_sn : nullptr;
+        DAVI_REQUIRE(put_strides(k_sb, k_sp, d, &sp.k_sb[j], &sp.k_sp[j]) &&
+                     put_strides(v_sb, v_sp, C, &sp.v_sb[j], &sp.v_sp[j]), "bad key/value strides");
+        gp.k_sb[j] = sp.k_sb[j]; gp.k_sp[j] = sp.k_sp[j]; gp.v_sb[j] = sp.v_sb[j]; gp.v_sp[j] = sp.v_sp[j];
     }
-    DwGeom g{}; g.q_sp = q_sp; g.k_sb = k_sb; g.k_sp = k_sp; g.v_sb = v_sb; g.v_sp = v_sp; g.o_sp = o_sp;
-    g.scale_ptr = scale;
-    return dw_bwd_impl(__func__, sp, gp, q, dout, dq, dscale, B, n, P, d, C, g, false,
-                       (cudaStream_t)stream);
+    DwGeom g{}; g.q_sp = q_sp; g.o_sp = o_sp; g.scale_ptr = scale;
+    return dw_bwd_impl(__func__, sp, gp, q, dout, dq, dscale, B, n, P, d, C, g, (cudaStream_t)stream);
 }
 
 extern "C" int davi_dw_attn_slots_fwd(const float* q, const float* const* k_ptrs,
-                                      const float* const* v_ptrs, float* out, float* attn, int B,
-                                      int n, int P, int d, int C, int64_t q_sp, int64_t k_sb,
-                                      int64_t k_sp, int64_t v_sb, int64_t v_sp, int64_t o_sp,
-                                      const float* scale, davi_stream_t stream) {
-    DAVI_REQUIRE(k_ptrs && v_ptrs, "null slot tables");
+                                      const float* const* v_ptrs, const int64_t* k_sps, const int64_t* v_sps,
+                                      float* out, float* attn, int B, int n, int P, int d, int C,
+                                      int64_t q_sp, int64_t o_sp, const float* scale, davi_stream_t stream) {
+    DAVI_REQUIRE(k_ptrs && v_ptrs && k_sps && v_sps, "null slot tables");
     DAVI_REQUIRE(n >= 1 && n <= DAVI_MAX_SLOTS, "n out of range");
     SlotPtrs sp{};
-    for (int j = 0; j < n; ++j) { sp.k[j] = k_ptrs[j]; sp.v[j] = v_ptrs[j]; }
-    DwGeom g{}; g.q_sp = q_sp; g.k_sb = k_sb; g.k_sp = k_sp; g.v_sb = v_sb; g.v_sp = v_sp; g.o_sp = o_sp;
-    g.scale_ptr = scale;
+    for (int j = 0; j < n; ++j) {
+        sp.k[j] = k_ptrs[j]; sp.v[j] = v_ptrs[j];
+        DAVI_REQUIRE(put_strides(k_sps[j] * P, k_sps[j], d, &sp.k_sb[j], &sp.k_sp[j]) &&
+                     put_strides(v_sps[j] * P, v_sps[j], C, &sp.v_sb[j], &sp.v_sp[j]), "bad slot strides");
+    }
+    DwGeom g{}; g.q_sp = q_sp; g.o_sp = o_sp; g.scale_ptr = scale;
     return dw_fwd_impl(__func__, sp, q, out, attn, B, n, P, d, C, g, (cudaStream_t)stream);
 }
 
 extern "C" int davi_dw_attn_slots_bwd(const float* q, const float* const* k_ptrs,
-                                      const float* const* v_ptrs, const float* dout, float* dq,
-                                      float* const* dk_ptrs, float* const* dv_ptrs, float* dscale,
-                                      int B, int n, int P, int d, int C, int64_t q_sp, int64_t k_sb,
-                                      int64_t k_sp, int64_t v_sb, int64_t v_sp, int64_t o_sp,
-                                      const float* scale, int accumulate, davi_stream_t stream) {
-    DAVI_REQUIRE(k_ptrs && v_ptrs && dk_ptrs && dv_ptrs, "null slot tables");
+                                      const float* const* v_ptrs, const int64_t* k_sps, const int64_t* v_sps,
+                                      const float* dout, float* dq, float* const* dk_ptrs, float* const* dv_ptrs,
+                                      const int64_t* dk_sps, const int64_t* dv_sps, float* dscale, int B, int n,
+                                      int P, int d, int C, int64_t q_sp, int64_t o_sp, const float* scale,
+                                      uint32_t accumulate_mask, davi_stream_t stream) {
+    DAVI_REQUIRE(k_ptrs && v_ptrs && k_sps && v_sps && dk_ptrs && dv_ptrs && dk_sps && dv_sps, "null slot tables");
     DAVI_REQUIRE(n >= 1 && n <= DAVI_MAX_SLOTS, "n out of range");
     SlotPtrs sp{}; SlotGradPtrs gp{};
     for (int j = 0; j < n; ++j) {
         sp.k[j] = k_ptrs[j]; sp.v[j] = v_ptrs[j];
         gp.dk[j] = dk_ptrs[j]; gp.dv[j] = dv_ptrs[j];
+        DAVI_REQUIRE(put_strides(k_sps[j] * P, k_sps[j], d, &sp.k_sb[j], &sp.k_sp[j]) &&
+                     put_strides(v_sps[j] * P, v_sps[j], C, &sp.v_sb[j], &sp.v_sp[j]), "bad slot strides");
+        DAVI_REQUIRE((!gp.dk[j] || put_strides(dk_sps[j] * P, dk_sps[j], d, &gp.k_sb[j], &gp.k_sp[j])) &&
+                     (!gp.dv[j] || put_strides(dv_sps[j] * P, dv_sps[j], C, &gp.v_sb[j], &gp.v_sp[j])),
+                     "bad slot gradient strides");
     }
-    DwGeom g{}; g.q_sp = q_sp; g.k_sb = k_sb; g.k_sp = k_sp; g.v_sb = v_sb; g.v_sp = v_sp; g.o_sp = o_sp;
-    g.scale_ptr = scale;
-    return dw_bwd_impl(__func__, sp, gp, q, dout, dq, dscale, B, n, P, d, C, g, accumulate != 0,
-                       (cudaStream_t)stream);
+    DwGeom g{}; g.q_sp = q_sp; g.o_sp = o_sp; g.scale_ptr = scale; g.acc_mask = accumulate_mask;
+    return dw_bwd_impl(__func__, sp, gp, q, dout, dq, dscale, B, n, P, d, C, g, (cudaStream_t)stream);
 }

@@ -65,6 +65,11 @@ class DepthWiseAttention(nn.Module):
         values [B,n,W,H,C] -> [B,W,H,C] (one fused kernel, no Permute copies)."""
         return ops.dw_attn(query, keys, values, self.scale)
 
+    def apply_ctx(self, query, slots):
+        """The same contraction over a slot list of ("kv", key, value) pairs and ("own"/"acc",
+        ops.SharedSlot) contexts shared with other layers (lazy gradient gather)."""
+        return ops.dw_attn_ctx(query, slots, self.scale)
+
     def apply_slots(self, query, keys, values):
         """Same contraction over python lists of per-layer tensors (the
         tf.stack of vae.py:340,350 never happens)."""
@@ -116,16 +121,20 @@ class NonlocalResNetBlock(nn.Module):
                 bs.append(bs[0].new_zeros(pad))
         w = torch.cat(ws, 0).contiguous(memory_format=torch.channels_last)
         b = torch.cat(bs, 0) if bs[0] is not None else None
-        qkv = to_nhwc(torch.nn.functional.conv2d(to_nchw(x), w, b))        # att.py:310,346,362
-        return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        return to_nhwc(torch.nn.functional.conv2d(to_nchw(x), w, b))       # att.py:310,346,362  [B,H,W,2d+C(+pad)]
 
     def forward(self, inputs):
         orig = inputs
         if self._use_ln:
             inputs = ops.layer_norm(inputs, self.ln_a_gamma, self.ln_a_beta)         # att.py:293-294
-        q, k, v = self._qkv(inputs)
+        qkv = self._qkv(inputs)
         x = inputs if not self._pad else torch.nn.functional.pad(inputs, (0, self._pad))
-        y = ops.nonlocal_attn(q, k, v, x, self._alignment_function.scale, self.gamma)  # att.py:358-389
+        d = self._key_dim
+        if d % 4 == 0:
+            y = ops.nonlocal_attn_packed(qkv, x, d, self._alignment_function.scale, self.gamma)   # att.py:358-389
+        else:   # odd key widths: slices are copied into 16-byte-aligned rows by the op
+            y = ops.nonlocal_attn(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], x,
+                                  self._alignment_function.scale, self.gamma)
         if self._pad:
             y = y[..., :self._C].contiguous()
         if not self._use_ln:

@@ -38,10 +38,15 @@ class WNConv2d(nn.Module):
         else:
             self.bias = None
         self.lambda_reg = lambda_reg
+        # set by util/trainer.py: a leaf view into the flat effective-weight array that ONE fused
+        # kernel (davi_weight_norm_fwd) fills for all convolutions of the model before the forward
+        self._w_override = None
 
     def kernel(self):
         if not self.use_weight_norm:
             return self.v
+        if self._w_override is not None:
+            return self._w_override
         # tf.nn.l2_normalize: v * rsqrt(max(sum v^2, 1e-12))                     weight_norm.py:133-134
         ss = self.v.square().sum(dim=(1, 2, 3), keepdim=True).clamp_min(1e-12)
         return self.v * (torch.exp(self.log_g).view(-1, 1, 1, 1) * torch.rsqrt(ss))

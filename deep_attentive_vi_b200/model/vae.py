@@ -182,15 +182,27 @@ class DeepVAE(nn.Module):
         h, c, kl = [None] * L, [None] * L, [None] * L
         q_logp, p_logp = [None] * L, [None] * L
         want_logp = compute_q_logp or compute_p_logp
+        # The reference stacks e[i:] / c[:i] for every layer (vae.py:339-350).  Here every tensor that
+        # several layers attend to is wrapped ONCE in a SharedSlot (values || key): the earliest consumer
+        # owns its gradient, the later ones accumulate into it from their backward kernels.
+        enc_att, dec_att = self._encoder_attention_hparams, self._decoder_attention_hparams
+        if enc_att is not None:
+            f = e[1].shape[-1] - enc_att.key_dim
+            e_shared = [None] + [ops.SharedSlot(t, f) for t in e[1:]]
+        c_shared = [None] * L
         for i in range(L):                                                              # vae.py:336-365
-            condition = e[i:] if self._encoder_attention_hparams is not None else e[i]  # vae.py:339-342
+            if enc_att is not None:                                                     # vae.py:339-342
+                condition = [e[i]] + [("own" if i == 0 else "acc", s) for s in e_shared[i + 1:]]
+            else:
+                condition = e[i]
             context = None
             if i > 0:
-                if self._decoder_attention_hparams is not None:
+                if dec_att is not None:
                     if i > 1:
                         g, b = self._ctx_layer_norm[i]
                         c[i - 2] = ops.layer_norm(c[i - 2], g, b)                       # vae.py:347-348
-                    context = c[:i]                                                     # vae.py:350
+                        c_shared[i - 2] = ops.SharedSlot(c[i - 2], c[i - 2].shape[-1] - dec_att.key_dim)
+                    context = [("own" if k == i - 2 else "acc", c_shared[k]) for k in range(i - 1)] + [c[i - 1]]  # vae.py:350
                 else:
                     context = c[i - 1]
             h[i], c[i], kl[i], q_logp[i], p_logp[i] = self._latent_layer[i].infer_top_down(

@@ -121,14 +121,17 @@ class VariationalLayer(nn.Module):
     def call_decoder(self, training, latent_condition=None, context=None, num_samples=1):
         """vl.py:338-418.  `context` is the LIST c[0..i-1] of [B,H,W,values||key]
         tensors (the reference receives tf.stack of it)."""
-        keys = values = None
         ctx_in = context
+        slots = None
         if self._use_decoder_attention:
+            # `context` = slot list: ("own"/"acc", SharedSlot) for c[0..i-2] (already layer-normed,
+            # vae.py:346-348) and, last, the raw tensor c[i-1]
             qd = self._decoder_attention_hparams.query_dim
-            nv = context[-1].shape[-1] - qd                                                 # vl.py:358
-            values = [c[..., :nv] for c in context]                                         # vl.py:359 (views)
-            keys = [c[..., nv:] for c in context]
-            ctx_in = values[-1]                                                             # vl.py:360
+            last = context[-1]
+            nv = last.shape[-1] - qd                                                        # vl.py:358
+            slots = list(context[:-1])
+            last_values, last_key = last[..., :nv], last[..., nv:]                          # vl.py:359 (views)
+            ctx_in = last_values                                                            # vl.py:360
         new_context = self.compute_context(latent_condition, ctx_in, training, num_samples)
         key = query = None
         if self._use_decoder_attention:
@@ -145,8 +148,9 @@ class VariationalLayer(nn.Module):
         if self._use_decoder_attention:
             if self._dec_ln:
                 new_context = ops.ln_gelu_residual(new_context, self.ctx_ln_gamma, self.ctx_ln_beta)  # vl.py:393-394
-                values = values[:-1] + [ops.layer_norm(values[-1], self.attn_ln_gamma, self.attn_ln_beta)]  # vl.py:396-401
-            att = self._decoder_attention.apply_slots(query, keys, values)                  # vl.py:403-406
+                last_values = ops.layer_norm(last_values, self.attn_ln_gamma, self.attn_ln_beta)      # vl.py:396-401
+            slots.append(("kv", last_key, last_values))
+            att = self._decoder_attention.apply_ctx(query, slots)                           # vl.py:403-406
             if self._dec_ln:
                 att = ops.ln_gelu_residual(att, self.attn_ln2_gamma, self.attn_ln2_beta)    # vl.py:408-409
             prior_condition = new_context + self._gamma * att                               # vl.py:412
@@ -166,12 +170,10 @@ class VariationalLayer(nn.Module):
         not_first = latent_condition is not None
         if not_first:
             self._prior_network.call(prior_condition, training)                             # vl.py:463
-        keys = values = None
         if self._use_encoder_attention:
+            # `condition` = [e[i] tensor, then ("own"/"acc", SharedSlot) for e[i+1..L]]
             f = self._enc_f
-            values = [e[..., :f] for e in condition]                                        # vl.py:472 (views)
-            keys = [e[..., f:] for e in condition]
-            cond = values[0]                                                                # vl.py:473
+            cond, key0 = condition[0][..., :f], condition[0][..., f:]                       # vl.py:472-473 (views)
         else:
             cond = condition
         if not_first:
@@ -179,15 +181,13 @@ class VariationalLayer(nn.Module):
         if self._use_encoder_attention:
             if not_first:
                 f = self._enc_f
-                cond, new_key = cond[..., :f], cond[..., f:]                                # vl.py:483
-                values = [cond] + values[1:]                                                # vl.py:486-488
-                keys = [new_key] + keys[1:]                                                 # vl.py:492-494
-            att = self._encoder_attention.apply_slots(enc_query, keys, values)              # vl.py:496-499
+                cond, key0 = cond[..., :f], cond[..., f:]                                   # vl.py:483-494
+            att = self._encoder_attention.apply_ctx(enc_query, [("kv", key0, cond)] + list(condition[1:]))  # vl.py:496-499
             if self._enc_ln:
                 att = ops.ln_gelu_residual(att, self.enc_ln_gamma, self.enc_ln_beta)        # vl.py:502
                 cond = ops.ln_gelu_residual(cond, self.cond_ln_gamma, self.cond_ln_beta)    # vl.py:503
             cond = cond + self._encoder_gamma * att                                         # vl.py:505
-            cond = torch.cat([cond, keys[0]], dim=-1)                                       # vl.py:507
+            cond = torch.cat([cond, key0], dim=-1)                                          # vl.py:507
         n_post, n_prior = noise if noise is not None else (None, None)
         prior = self._prior_network if (not_first and self._residual) else None
         if not_first and not self._residual:

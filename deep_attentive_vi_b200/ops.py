@@ -120,67 +120,139 @@ def dw_attn_weights(query, keys, scale=None):
 # R1/R2/R3: depth-wise attention over a list of slots (no stack / split copies)
 # ---------------------------------------------------------------------------
 
+class SharedSlot:
+    """A per-layer tensor [B,H,W,nv+d] (values || key along the channel axis) that several LATER
+    layers attend to.  Its gradient is gathered lazily: every consumer's backward kernel adds its
+    contribution straight into one buffer (`accumulate_mask` of davi_dw_attn_slots_bwd) instead of
+    producing a zero-filled full-size slice gradient that autograd then sums (what TF's add_n over
+    the L-1 consumers does).  Exactly one consumer -- the EARLIEST layer in forward
+    order, whose backward runs last -- takes the tensor as a real autograd input ("own") and hands
+    the finished buffer back as its gradient; all later layers use it detached ("acc")."""
+
+    def __init__(self, tensor, nv):
+        self.tensor = tensor if tensor.is_contiguous() else tensor.contiguous()
+        self.nv = nv
+        self.grad = None
+        self.closed = False
+
+
+def _slot_tables(spec, tensors, d, C):
+    """Pointer / stride tables of the forward operands.  Returns (k_ptrs, v_ptrs, k_sps, v_sps, keep)."""
+    kp, vp, ks, vs, keep = [], [], [], [], []
+    it = iter(tensors)
+    for item in spec:
+        if item[0] == "kv":
+            k, k_s = _rows(next(it))
+            v, v_s = _rows(next(it))
+            keep += [k, v]
+            kp.append(k.data_ptr()); vp.append(v.data_ptr()); ks.append(k_s); vs.append(v_s)
+        else:
+            sh = item[1]
+            if item[0] == "own":
+                next(it)                                   # the autograd-visible alias of sh.tensor
+            t = sh.tensor
+            ct = t.shape[-1]
+            assert ct == sh.nv + d and sh.nv == C, "shared slot must be values || key"
+            keep.append(t)
+            kp.append(t.data_ptr() + 4 * sh.nv); vp.append(t.data_ptr()); ks.append(ct); vs.append(ct)
+    return kp, vp, ks, vs, keep
+
+
 class _DwAttnSlots(torch.autograd.Function):
-    """inputs: query, scale, n, then k_0..k_{n-1}, v_0..v_{n-1} (views allowed)."""
+    """inputs: query, scale, spec, then the autograd-visible tensors named by spec:
+    ("kv",) -> key, value;  ("own", shared) -> shared.tensor;  ("acc", shared) -> nothing."""
 
     @staticmethod
-    def forward(ctx, query, scale, n, *kv):
-        ks, vs = kv[:n], kv[n:]
-        _require_cuda(query, scale, *ks, *vs)
-        B, H, W, d = ks[0].shape
-        C = vs[0].shape[-1]
+    def forward(ctx, query, scale, spec, *tensors):
+        _require_cuda(query, scale, *tensors)
+        n = len(spec)
+        B, H, W = query.shape[0], query.shape[1], query.shape[2]
+        d = query.shape[-1]
+        C = tensors[1].shape[-1] if spec[0][0] == "kv" else spec[0][1].nv
         P = H * W
         q, q_sp = _rows(query)
-        # every slot must share one (batch, pixel) stride pair
-        ks = [_rows(t)[0] for t in ks]
-        vs = [_rows(t)[0] for t in vs]
-        k_sp, v_sp = ks[0].stride(-2), vs[0].stride(-2)
-        if any(t.stride(-2) != k_sp for t in ks):
-            ks = [t.contiguous() for t in ks]; k_sp = d
-        if any(t.stride(-2) != v_sp for t in vs):
-            vs = [t.contiguous() for t in vs]; v_sp = C
+        kp, vp, ks, vs, keep = _slot_tables(spec, tensors, d, C)
         out = torch.empty((B, H, W, C), device=q.device, dtype=torch.float32)
         s_t, s_ptr = _scalar_ptr(scale, q)
-        kt, ka = _lib.ptr_table([t.data_ptr() for t in ks])
-        vt, va = _lib.ptr_table([t.data_ptr() for t in vs])
-        _lib_call("davi_dw_attn_slots_fwd", _p(q), kt, vt, _p(out), 0, B, n, P, d, C,
-                  q_sp, P * k_sp, k_sp, P * v_sp, v_sp, C, s_ptr, _stream())
-        ctx.save_for_backward(q, s_t, *ks, *vs)
-        ctx.dims = (B, n, P, d, C, q_sp, k_sp, v_sp)
+        kt, ka = _lib.ptr_table(kp)
+        vt, va = _lib.ptr_table(vp)
+        kst, ksa = _lib.int_table(ks)
+        vst, vsa = _lib.int_table(vs)
+        _lib_call("davi_dw_attn_slots_fwd", _p(q), kt, vt, kst, vst, _p(out), 0, B, n, P, d, C,
+                  q_sp, C, s_ptr, _stream())
+        ctx.save_for_backward(q, s_t, *keep)
+        ctx.spec = spec
+        ctx.dims = (B, n, P, d, C, q_sp, kp, vp, ks, vs)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        B, n, P, d, C, q_sp, k_sp, v_sp = ctx.dims
+        B, n, P, d, C, q_sp, kp, vp, ks, vs = ctx.dims
+        spec = ctx.spec
         saved = ctx.saved_tensors
         q, s_t = saved[0], saved[1]
-        ks, vs = saved[2:2 + n], saved[2 + n:]
         dout = dout.contiguous()
-        dq = torch.empty(q.shape, device=q.device, dtype=torch.float32)
-        dks = [torch.empty(t.shape, device=q.device, dtype=torch.float32) for t in ks]
-        dvs = [torch.empty(t.shape, device=q.device, dtype=torch.float32) for t in vs]
+        dev = q.device
+        dq = torch.empty(q.shape, device=dev, dtype=torch.float32)   # dense rows
+        dq_view, dq_sp = dq, d
+        if q_sp != d:   # the query was a channel-slice view: give the kernel a dense copy of it
+            q = q.contiguous(); q_sp = d
         need_ds = s_t is not None and ctx.needs_input_grad[1]
-        dscale = torch.empty((), device=q.device, dtype=torch.float32) if need_ds else None
-        # gradients are dense, so they get their own strides: run the kernel on dense
-        # copies of strided inputs only when needed (contiguous slots are the fast path)
-        if q_sp != d or k_sp != d or v_sp != C:
-            q = q.contiguous(); ks = [t.contiguous() for t in ks]; vs = [t.contiguous() for t in vs]
-            q_sp, k_sp, v_sp = d, d, C
-        kt, ka = _lib.ptr_table([t.data_ptr() for t in ks])
-        vt, va = _lib.ptr_table([t.data_ptr() for t in vs])
-        dkt, dka = _lib.ptr_table([t.data_ptr() for t in dks])
-        dvt, dva = _lib.ptr_table([t.data_ptr() for t in dvs])
-        _lib_call("davi_dw_attn_slots_bwd", _p(q), kt, vt, _p(dout), _p(dq), dkt, dvt, _p(dscale),
-                  B, n, P, d, C, q_sp, P * k_sp, k_sp, P * v_sp, v_sp, C, _p(s_t), 0, _stream())
-        return (dq, dscale, None, *dks, *dvs)
+        dscale = torch.empty((), device=dev, dtype=torch.float32) if need_ds else None
+        dkp, dvp, dks, dvs, grads, mask = [], [], [], [], [], 0
+        lead = dout.shape[:-1]
+        for j, item in enumerate(spec):
+            if item[0] == "kv":
+                dk = torch.empty((*lead, d), device=dev, dtype=torch.float32)
+                dv = torch.empty((*lead, C), device=dev, dtype=torch.float32)
+                grads += [dk, dv]
+                dkp.append(dk.data_ptr()); dvp.append(dv.data_ptr()); dks.append(d); dvs.append(C)
+            else:
+                sh = item[1]
+                assert not sh.closed, "shared context consumed after its owner's backward ran"
+                if sh.grad is None:
+                    sh.grad = torch.empty_like(sh.tensor)            # first touch overwrites: no memset
+                else:
+                    mask |= 1 << j
+                ct = sh.tensor.shape[-1]
+                dkp.append(sh.grad.data_ptr() + 4 * sh.nv); dvp.append(sh.grad.data_ptr())
+                dks.append(ct); dvs.append(ct)
+                if item[0] == "own":
+                    grads.append(sh.grad)
+                    sh.closed = True
+        kt, ka = _lib.ptr_table(kp)
+        vt, va = _lib.ptr_table(vp)
+        kst, ksa = _lib.int_table(ks)
+        vst, vsa = _lib.int_table(vs)
+        dkt, dka = _lib.ptr_table(dkp)
+        dvt, dva = _lib.ptr_table(dvp)
+        dkst, dksa = _lib.int_table(dks)
+        dvst, dvsa = _lib.int_table(dvs)
+        _lib_call("davi_dw_attn_slots_bwd", _p(q), kt, vt, kst, vst, _p(dout), _p(dq), dkt, dvt, dkst, dvst,
+                  _p(dscale), B, n, P, d, C, q_sp, C, _p(s_t), mask, _stream())
+        return (dq_view, dscale, None, *grads)
+
+
+def dw_attn_ctx(query, slots, scale=None):
+    """Depth-wise attention over a list of slots, each one of
+        ("kv", key [B,H,W,d], value [B,H,W,C])   tensors of this layer (views allowed, no copies)
+        ("own", SharedSlot) / ("acc", SharedSlot) a context shared with other layers (see SharedSlot)."""
+    spec, tensors = [], []
+    for item in slots:
+        if item[0] == "kv":
+            spec.append(("kv",)); tensors += [item[1], item[2]]
+        elif item[0] == "own":
+            spec.append(("own", item[1])); tensors.append(item[1].tensor)
+        else:
+            spec.append(("acc", item[1]))
+    return _DwAttnSlots.apply(query, scale, tuple(spec), *tensors)
 
 
 def dw_attn_slots(query, keys, values, scale=None):
     """query [B,H,W,d]; keys/values: lists of n tensors [B,H,W,d] / [B,H,W,C]
     (channel-slice views of wider tensors are passed without copying)."""
-    n = len(keys)
-    assert n == len(values) and n >= 1
-    return _DwAttnSlots.apply(query, scale, n, *keys, *values)
+    assert len(keys) == len(values) and len(keys) >= 1
+    return dw_attn_ctx(query, [("kv", k, v) for k, v in zip(keys, values)], scale)
 
 
 # ---------------------------------------------------------------------------
@@ -290,6 +362,55 @@ def nonlocal_attn(q, k, v, x, scale, gamma):
         xp = torch.nn.functional.pad(x, (0, pad))
         return _NonlocalAttn.apply(q, k, v, xp, scale, gamma)[..., :C]
     return _NonlocalAttn.apply(q, k, v, x, scale, gamma)
+
+
+class _NonlocalAttnPacked(torch.autograd.Function):
+    """Same op on the PACKED projection output qkv [B,H,W,2d+C] (q | k | v along the channel axis):
+    the kernels read the three column slices through strides and write dq | dk | dv straight into
+    one packed gradient tensor, so neither forward slices nor backward zero-fill/add copies exist."""
+
+    @staticmethod
+    def forward(ctx, qkv, x, d, scale, gamma):
+        _require_cuda(qkv, x, scale, gamma)
+        B, C = x.shape[0], x.shape[-1]
+        N = x.numel() // (B * C)
+        rs = qkv.shape[-1]
+        assert rs == 2 * d + C and d % 4 == 0 and C % 4 == 0
+        qkv = qkv.contiguous()
+        xr, x_s = _rows(x)
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        lse = torch.empty((B, N), device=x.device, dtype=torch.float32)
+        o_save = torch.empty((B, N, C), device=x.device, dtype=torch.float32)
+        s_t, s_ptr = _scalar_ptr(scale, x)
+        g_t, g_ptr = _scalar_ptr(gamma, x)
+        p = qkv.data_ptr()
+        _lib_call("davi_nonlocal_attn_fwd", p, p + 4 * d, p + 8 * d, _p(xr), _p(y), _p(lse), _p(o_save), B, N, d, C,
+                  rs, rs, rs, x_s, C, C, s_ptr, g_ptr, _stream())
+        ctx.save_for_backward(qkv, lse, o_save, s_t, g_t)
+        ctx.cfg = (B, N, d, C, rs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        qkv, lse, o_save, s_t, g_t = ctx.saved_tensors
+        B, N, d, C, rs = ctx.cfg
+        dy = dy.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dgs = torch.empty(2, device=dy.device, dtype=torch.float32)
+        wsb = _lib.load().davi_nonlocal_attn_bwd_workspace_bytes(B, N, d, C)
+        ws = torch.empty(max(wsb // 4, 1), device=dy.device, dtype=torch.float32)
+        p, g = qkv.data_ptr(), dqkv.data_ptr()
+        _lib_call("davi_nonlocal_attn_bwd", p, p + 4 * d, p + 8 * d, _p(lse), _p(o_save), _p(dy), g, g + 4 * d,
+                  g + 8 * d, _p(dgs), B, N, d, C, rs, rs, rs, C, C, _p(s_t), _p(g_t), _p(ws), wsb, _stream())
+        dscale = dgs[1] if (s_t is not None and ctx.needs_input_grad[3]) else None
+        dgamma = dgs[0] if ctx.needs_input_grad[4] else None
+        return dqkv, dy, None, dscale, dgamma
+
+
+def nonlocal_attn_packed(qkv, x, d, scale, gamma):
+    """y = gamma * softmax(scale * q k^T) v + x with q | k | v packed along the last axis of
+    qkv [B,H,W,2d+C] (the output of the fused 1x1 projection); x [B,H,W,C], C % 4 == 0."""
+    return _NonlocalAttnPacked.apply(qkv, x, d, scale, gamma)
 
 
 # ---------------------------------------------------------------------------

@@ -98,6 +98,47 @@ class FlatState:
                 off += pad(n)
             self.segments.append((float(l2), start, off - start))
         assert off == size
+        self._build_weight_norm(model, device, pad)
+
+    def _build_weight_norm(self, model, device, pad):
+        """Flat effective-weight array W (+ its gradient dW) and the device row tables of
+        davi_weight_norm_fwd/bwd: every weight-normed conv reads its kernel from a leaf view of W."""
+        from ..layers.weight_norm import WNConv2d
+        mods = [m for m in model.modules() if isinstance(m, WNConv2d) and m.use_weight_norm]
+        self.wn_rows = 0
+        if not mods:
+            return
+        base = self.P.data_ptr()
+        rv, rg, rw, rc = [], [], [], []
+        woff = 0
+        sizes = []
+        for m in mods:
+            o, i, h, w = m.v.shape
+            cols = i * h * w
+            v_off = (m.v.data_ptr() - base) // 4
+            g_off = (m.log_g.data_ptr() - base) // 4
+            for r in range(o):
+                rv.append(v_off + r * cols); rg.append(g_off + r); rw.append(woff + r * cols); rc.append(cols)
+            sizes.append((m, woff, o, i, h, w))
+            woff += pad(o * cols)
+        self.W = torch.zeros(woff, device=device)
+        self.dW = torch.zeros(woff, device=device)
+        for m, off, o, i, h, w in sizes:
+            n = o * i * h * w
+            wv = self.W[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)       # OHWI memory = channels_last
+            wv.requires_grad_(True)
+            wv.grad = self.dW[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)
+            m._w_override = wv
+        t64 = lambda v: torch.tensor(v, dtype=torch.int64, device=device)
+        self.wn_tables = (t64(rv), t64(rg), t64(rw), torch.tensor(rc, dtype=torch.int32, device=device))
+        self.wn_rows = len(rv)
+        self.wn_modules = [s[0] for s in sizes]
+
+    def release(self):
+        """Detach the model from the fused weight-norm path (it computes its kernels itself again)."""
+        for m in getattr(self, "wn_modules", []):
+            m._w_override = None
+        self.wn_rows = 0
 
 
 class Trainer:
@@ -144,10 +185,19 @@ class Trainer:
     def forward_backward(self, x, eps=None, noise=None):
         st = self.state
         st.G.zero_()
+        stream = torch.cuda.current_stream().cuda_stream
+        if st.wn_rows:                                               # all conv kernels: v, log_g -> W
+            st.dW.zero_()
+            rv, rg, rw, rc = st.wn_tables
+            _lib.call("davi_weight_norm_fwd", st.P.data_ptr(), st.W.data_ptr(), rv.data_ptr(), rg.data_ptr(),
+                      rw.data_ptr(), rc.data_ptr(), st.wn_rows, stream)
         nll, kl, nelbo = self.model(x, True, eps, noise)
         global_batch = x.shape[0] * self.world                       # tr.py:174
         loss = (nll.sum() + self.beta_dev * kl.sum()) * (1.0 / global_batch)
         loss.backward()
+        if st.wn_rows:                                               # dW -> grads of v and log_g
+            _lib.call("davi_weight_norm_bwd", st.P.data_ptr(), st.dW.data_ptr(), st.G.data_ptr(), rv.data_ptr(),
+                      rg.data_ptr(), rw.data_ptr(), rc.data_ptr(), st.wn_rows, stream)
         return nll, kl
 
     def all_reduce(self):

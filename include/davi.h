@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DAVI_VERSION 101          /* major*100 + minor */
+#define DAVI_VERSION 102          /* major*100 + minor */
 #define DAVI_MAX_SLOTS 32         /* max stacked layers n of the depth-wise attention */
 
 #define DAVI_OK 0
@@ -92,28 +92,36 @@ int davi_dw_attn_bwd(const float* q, const float* keys, const float* values,
  * R1/R2/R3  Depth-wise attention over a LIST of context slots (no tf.stack).
  * Replaces the stack -> split -> unstack/stack -> apply sequence of
  * model/vae.py:339-350 + model/variational_layer.py:357-360,396-406,472-499:
- * slot j contributes keys k_ptrs[j] [B,P,d] and values v_ptrs[j] [B,P,C], all
- * slots sharing (k_sb,k_sp) / (v_sb,v_sp).  k_ptrs / v_ptrs are HOST arrays of
- * n device pointers (copied into the launch arguments, not retained).
+ * slot j contributes keys k_ptrs[j] [B,P,d] and values v_ptrs[j] [B,P,C] with its
+ * OWN pixel strides k_sps[j] / v_sps[j] (floats; batch stride = P * pixel stride),
+ * so a slot may be a channel slice of a wider per-layer tensor (values || key)
+ * or a dense fresh tensor -- nothing is ever copied into a stacked layout.
+ * k_ptrs / v_ptrs / k_sps / v_sps are HOST arrays of n entries (copied into the
+ * launch arguments, not retained).
  * ---------------------------------------------------------------------- */
 int davi_dw_attn_slots_fwd(const float* q, const float* const* k_ptrs,
-                           const float* const* v_ptrs, float* out, float* attn,
+                           const float* const* v_ptrs,
+                           const int64_t* k_sps, const int64_t* v_sps,
+                           float* out, float* attn,
                            int B, int n, int P, int d, int C,
-                           int64_t q_sp, int64_t k_sb, int64_t k_sp,
-                           int64_t v_sb, int64_t v_sp, int64_t o_sp,
+                           int64_t q_sp, int64_t o_sp,
                            const float* scale, davi_stream_t stream);
 
-/* accumulate != 0: dk_ptrs[j] / dv_ptrs[j] are read-modify-written (+=) so one
- * gradient buffer per context collects the contributions of every later layer
- * (replaces TF's add_n over the L-1 consumers).  A NULL entry skips that slot. */
+/* Gradient.  dk_ptrs[j] / dv_ptrs[j] (pixel strides dk_sps[j] / dv_sps[j]) are
+ * OVERWRITTEN, or read-modify-written (+=) when bit j of accumulate_mask is set:
+ * one gradient buffer per context then collects the contributions of every
+ * later layer directly (replaces TF's add_n over the L-1 consumers and the
+ * zero-filled slice gradients).  A NULL entry skips that slot. */
 int davi_dw_attn_slots_bwd(const float* q, const float* const* k_ptrs,
-                           const float* const* v_ptrs, const float* dout,
+                           const float* const* v_ptrs,
+                           const int64_t* k_sps, const int64_t* v_sps,
+                           const float* dout,
                            float* dq, float* const* dk_ptrs, float* const* dv_ptrs,
+                           const int64_t* dk_sps, const int64_t* dv_sps,
                            float* dscale,
                            int B, int n, int P, int d, int C,
-                           int64_t q_sp, int64_t k_sb, int64_t k_sp,
-                           int64_t v_sb, int64_t v_sp, int64_t o_sp,
-                           const float* scale, int accumulate, davi_stream_t stream);
+                           int64_t q_sp, int64_t o_sp,
+                           const float* scale, uint32_t accumulate_mask, davi_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * R2/R3 glue: LayerNormalization(epsilon) over the last axis, optionally with
@@ -256,6 +264,24 @@ int davi_adamax_step(float* param, const float* grad, float* m, float* u, int64_
 int davi_adamax_step_dev(float* param, const float* grad, float* m, float* u, int64_t n,
                          const float* hyper, float beta1, float beta2, float eps, float l2,
                          davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * 8(f1)  Weight normalisation of every convolution kernel of the model in one
+ * launch.  Replaces WeightNorm._compute_weights (layers/weight_norm.py:126-135)
+ *   kernel[o,:] = v[o,:] * exp(log_g[o]) * rsqrt(max(sum_k v[o,k]^2, 1e-12))
+ * over the flat parameter array of util/trainer.py.  The four DEVICE tables
+ * name each of the `rows` output-channel rows: offset of its v row and of its
+ * log_g scalar inside params, offset of the row inside the effective-weight
+ * array w, and its width (in floats).
+ * ---------------------------------------------------------------------- */
+int davi_weight_norm_fwd(const float* params, float* w,
+                         const int64_t* row_v, const int64_t* row_g, const int64_t* row_w,
+                         const int* row_cols, int64_t rows, davi_stream_t stream);
+/* Gradient: dw (laid out like w) -> grads (laid out like params): the v rows and
+ * the log_g scalars named by the tables are OVERWRITTEN. */
+int davi_weight_norm_bwd(const float* params, const float* dw, float* grads,
+                         const int64_t* row_v, const int64_t* row_g, const int64_t* row_w,
+                         const int* row_cols, int64_t rows, davi_stream_t stream);
 
 #ifdef __cplusplus
 }

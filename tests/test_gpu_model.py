@@ -29,7 +29,10 @@ def test_elbo_and_gradients_match_oracle(cuda, flags):
     oracle = OracleVAE(helpers.oracle_cfg(kw), m.state_dict())
     # oracle with autograd on two probe parameters
     probes = ["_latent_layer.2._gamma", "_latent_layer.1._encoder_gamma",
-              "_latent_layer.1._prior_network._params_network._conv2d_layers.0.v"]
+              "_latent_layer.1._prior_network._params_network._conv2d_layers.0.v",
+              # gradients that reach their weight THROUGH the shared contexts (lazy gradient gather):
+              "_latent_layer.0._decoder_const", "_preproc_encoder.0._stem_layer.v",
+              "_latent_layer.0._posterior_network._params_network._conv2d_layers.0.v"]
     for k in probes:
         oracle.sd[k].requires_grad_()
     nll_o, kl_o, nelbo_o = oracle.forward(x, eps, True, noise)

@@ -1,7 +1,6 @@
 #!/bin/bash
-# Round diagnostics on the GPU box: parity tests, nonlocal check, bench (graph), step profile.
+# Round diagnostics on the GPU box: parity tests, bench (graph), step profile.
 mkdir -p gpurun_out
-timeout 300 python tools/nl_check.py --bwd > gpurun_out/nl_check.jsonl 2>&1; echo "nl rc=$?"
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_graph.json 2> gpurun_out/bench_graph.err; echo "bench graph rc=$?"
 timeout 600 python tools/step_probe.py > gpurun_out/step_probe.txt 2>&1; echo "probe rc=$?"
