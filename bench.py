@@ -156,7 +156,10 @@ def dw_roofline(batch, device):
     from deep_attentive_vi_b200 import _lib
     L, d, HW, P = 16, 20, 16, 256
     stream = torch.cuda.current_stream().cuda_stream
+    # L2 flush before every timed launch: write 256 MB, then READ another 256 MB so that the cache is left
+    # full of clean lines (a write-only flush makes the timed kernel pay the write-back of the flush itself)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
+    flush_rd = torch.zeros(256 * 1024 * 1024 // 4, device=device)
     calls = [("dec", i, 276) for i in range(1, L)] + [("enc", L + 1 - i, 256) for i in range(L)]
     nmax = L + 1
     Cmax = 276
@@ -182,6 +185,7 @@ def dw_roofline(batch, device):
             ts = []
             for rep in range(4):
                 flush.fill_(0.0)
+                flush_rd.sum()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 _lib.call(name, *a)
@@ -286,7 +290,7 @@ def run_davi(args):
         "config": {"workload": WORKLOAD, "global_batch": B * world, "params": nparams,
                    "parallelism": f"dp{world}", "cuda_graph": not args.eager, "convs": "cuDNN fp32" if args.fp32_convs else "cuDNN tf32",
                    "l2": "inputs (2 GB activations per step) exceed L2; dw-attention roofline calls are "
-                         "timed after an explicit 256 MB L2 flush"},
+                         "timed after an explicit L2 flush (256 MB written, then 256 MB read)"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 32 * 3 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss")},
         "gpu_launches": launches,
@@ -299,7 +303,14 @@ def run_davi(args):
             ach = tb / tt / 1e6
             line["roofline"] = {"bound": "hbm", "kernel": "dw_attn_fwd/bwd (62 calls of one step)",
                                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": which, "traffic": None,
+                                "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": which,
+                                # ncu --set full, largest decoder call (n=15, C=276, B=40), DRAM read+write bytes
+                                # per launch next to the algorithmic bytes (profiles/r01_ncu_dw_attn_v1_summary.txt)
+                                "traffic": 187.6e6 + 319.1e6,
+                                "traffic_detail": {"launches": "dw_attn fwd + bwd, n=15", "fwd_dram_MB": 187.6,
+                                                   "bwd_dram_MB": 319.1, "fwd_algorithmic_MB": 194.0,
+                                                   "bwd_algorithmic_MB": 376.7,
+                                                   "note": "bwd writes partly still in L2 at kernel end"},
                                 "algorithmic_MB_per_step": tb / 1e6, "kernel_ms_per_step": tt}
             if args.roofline_detail:
                 with open(args.roofline_detail, "w") as f:
