@@ -41,6 +41,8 @@ SIGNATURES = {
     "davi_is_logsumexp": (_i, [_f, _f, _i, _i, _s]),
     "davi_weight_norm_fwd": (_i, [_f, _f, _f, _f, _f, _f, _l, _s]),
     "davi_weight_norm_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _l, _s]),
+    "davi_colsum_workspace_bytes": (_z, [_l, _i]),
+    "davi_colsum": (_i, [_f, _f, _l, _i, _l, _f, _z, _s]),
     "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
     "davi_adamax_step_dev": (_i, [_f, _f, _f, _f, _l, _f, _r, _r, _r, _r, _s]),
 }
@@ -84,7 +86,7 @@ def check(rc, what):
 
 # kernels launched by one successful call of each entry point (bench.py's
 # `gpu_launches` claim is the sum over the timed region)
-KERNELS_PER_CALL = {"davi_ln_gelu_bwd": 2, "davi_nonlocal_attn_bwd": 4}
+KERNELS_PER_CALL = {"davi_ln_gelu_bwd": 2, "davi_nonlocal_attn_bwd": 4, "davi_colsum": 2}
 _launches = 0
 
 

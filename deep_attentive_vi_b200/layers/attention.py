@@ -121,7 +121,7 @@ class NonlocalResNetBlock(nn.Module):
                 bs.append(bs[0].new_zeros(pad))
         w = torch.cat(ws, 0).contiguous(memory_format=torch.channels_last)
         b = torch.cat(bs, 0) if bs[0] is not None else None
-        return to_nhwc(torch.nn.functional.conv2d(to_nchw(x), w, b))       # att.py:310,346,362  [B,H,W,2d+C(+pad)]
+        return to_nhwc(ops.conv2d_bias(to_nchw(x), w, b))       # att.py:310,346,362  [B,H,W,2d+C(+pad)]
 
     def forward(self, inputs):
         orig = inputs

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .util import deep_vae_init_
 
 
@@ -64,11 +65,11 @@ class WNConv2d(nn.Module):
                 return tot // 2, tot - tot // 2
             (pt, pb), (pl, pr) = pads(H), pads(W)
             if pt == pb and pl == pr:
-                y = F.conv2d(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl))
+                y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl))
             else:
-                y = F.conv2d(F.pad(xc, (pl, pr, pt, pb)), self.kernel(), self.bias, stride=s)
+                y = ops.conv2d_bias(F.pad(xc, (pl, pr, pt, pb)), self.kernel(), self.bias, stride=s)
         else:
-            y = F.conv2d(xc, self.kernel(), self.bias, stride=s)
+            y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s)
         return to_nhwc(y)
 
     def reg_loss(self):

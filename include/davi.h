@@ -283,6 +283,14 @@ int davi_weight_norm_bwd(const float* params, const float* dw, float* grads,
                          const int64_t* row_v, const int64_t* row_g, const int64_t* row_w,
                          const int* row_cols, int64_t rows, davi_stream_t stream);
 
+/* Column sums of a channels-last tensor x [rows, C] (row stride x_s): out[c] =
+ * sum_r x[r,c], OVERWRITTEN.  The bias gradient of the Keras Conv2D layers
+ * (layers/resnet.py:589-601, use_bias=True).  C % 4 == 0.  Two launches: per-CTA
+ * partial rows into the workspace, then their sum (no same-address atomics). */
+size_t davi_colsum_workspace_bytes(int64_t rows, int C);
+int davi_colsum(const float* x, float* out, int64_t rows, int C, int64_t x_s,
+                void* workspace, size_t workspace_bytes, davi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

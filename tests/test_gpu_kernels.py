@@ -249,3 +249,31 @@ def test_full_size_properties_cifar_decoder_call(cuda):
     v2 = torch.randn_like(v)
     lin = ops.dw_attn(q, k, 2.0 * v + v2)
     assert torch.allclose(lin, 2.0 * out + ops.dw_attn(q, k, v2), atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,C", [(10240, 316), (10240, 276), (1000, 64), (7, 8), (40960, 140)])
+def test_colsum_matches_fp64(cuda, rows, C):
+    from deep_attentive_vi_b200 import ops
+    torch.manual_seed(rows + C)
+    g = torch.randn(rows, C, device=cuda)
+    got = ops.colsum_nhwc(g)
+    want = g.double().sum(0)
+    assert ((got.double() - want).abs().max() / want.abs().max()).item() < 1e-5
+
+
+def test_conv_bias_gradient_path_matches_autograd(cuda):
+    """ops.conv2d_bias (cuDNN conv + davi_colsum bias gradient) against plain autograd F.conv2d."""
+    from deep_attentive_vi_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    x = torch.randn(4, 16, 16, 24, device=cuda).permute(0, 3, 1, 2).requires_grad_()
+    w = torch.randn(32, 24, 3, 3, device=cuda).contiguous(memory_format=torch.channels_last).requires_grad_()
+    b = torch.randn(32, device=cuda, requires_grad=True)
+    go = torch.randn(4, 32, 16, 16, device=cuda).contiguous(memory_format=torch.channels_last)
+    y1 = ops.conv2d_bias(x, w, b, stride=1, padding=1)
+    g1 = torch.autograd.grad(y1, (x, w, b), go)
+    y2 = torch.nn.functional.conv2d(x, w, b, stride=1, padding=1)
+    g2 = torch.autograd.grad(y2, (x, w, b), go)
+    assert torch.allclose(y1, y2)
+    for a, c in zip(g1, g2):
+        assert ((a - c).abs().max() / c.abs().max()).item() < 1e-5

@@ -20,24 +20,25 @@ B = int(os.environ.get("B", 40))
 x = torch.randint(0, 256, (B, 32, 32, 3), device=dev).float()
 
 
+from deep_attentive_vi_b200.util.trainer import Trainer  # noqa: E402
+tr = Trainer(m, device=dev)
+
+
 def step():
-    nll, kl, _ = m(x, True)
-    loss = nll.mean() + kl.mean()
-    loss.backward()
-    return loss
+    return tr.train_step(x)
 
 
 for _ in range(3):
-    step(); m.zero_grad(set_to_none=True)
+    step()
 torch.cuda.synchronize()
 t = time.time()
 n = 5
 for _ in range(n):
-    step(); m.zero_grad(set_to_none=True)
+    step()
 torch.cuda.synchronize()
 dt = (time.time() - t) / n
 print(f"step {dt*1e3:.1f} ms  -> {B/dt:.1f} img/s (tf32={tf32}), mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
 from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=70))
