@@ -69,6 +69,10 @@ colsum_finish_kernel(const float* __restrict__ partial, float* __restrict__ out,
     }
 }
 
+}  // namespace davi
+
+using namespace davi;
+
 static void colsum_plan(int64_t rows, int C, int* ctas, int* rows_per_cta) {
     const int RL = kCsThreads / (C / 4);
     int n = 2 * 148;
