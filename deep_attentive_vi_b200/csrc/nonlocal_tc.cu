@@ -23,6 +23,8 @@
 // Instruction cost measured by tools/umma_probe2.cu (profiles/r01_umma_probe2.txt):
 // ~173 cycles per SS MMA, ~115 per TS MMA, independent of N <= 160.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "davi_common.cuh"
 #include "tc_common.cuh"
@@ -76,10 +78,8 @@ __device__ __forceinline__ void lo_pass(const uint8_t* raw, uint8_t* lo, int n_f
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kPvThreads, 1)
-nl_pv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-             const __grid_constant__ CUtensorMap tmW, const PvArgs a, const PvGeom g) {
-    extern __shared__ uint8_t smem_raw[];
+__device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmW,
+                                           const PvArgs& a, const PvGeom& g, uint8_t* smem_raw) {
     __shared__ PvBars bars;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -123,7 +123,7 @@ nl_pv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     }
     if (warp == 10) tmem_alloc(&bars.tmem_base, 512);
     if (MODE == 1)
-        for (int i = tid; i < g.N; i += kPvThreads) sStats[i] = a.lse_in[(int64_t)b * g.N + i] * kLog2e;
+        for (int i = tid; i < g.N; i += blockDim.x) sStats[i] = a.lse_in[(int64_t)b * g.N + i] * kLog2e;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -251,7 +251,7 @@ nl_pv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp == 10) {
         if (lane == 0) {
             // =================================================================
             // MMA issuer (one thread)
@@ -331,7 +331,7 @@ nl_pv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const int C4 = g.C >> 2, ld = g.Cp + 4;
         const float* tile = reinterpret_cast<const float*>(smem);
         const int64_t row0 = (int64_t)b * g.N + r0;
-        for (int idx = tid; idx < kPvM * C4; idx += kPvThreads) {
+        for (int idx = tid; idx < kPvM * C4; idx += blockDim.x) {
             const int rr = idx / C4, c = (idx - rr * C4) * 4;
             const float4 o = *reinterpret_cast<const float4*>(tile + (size_t)rr * ld + c);
             if (MODE == 0) {
@@ -346,6 +346,14 @@ nl_pv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             }
         }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPvThreads, 1)
+nl_pv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmW, const PvArgs a, const PvGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    nl_pv_body<MODE>(tmX, tmY, tmW, a, g, smem_raw);
 }
 
 // =============================================================================
@@ -384,11 +392,9 @@ struct DsBars {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kDsThreads, 1)
-nl_ds_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-             const __grid_constant__ CUtensorMap tmYmn, const __grid_constant__ CUtensorMap tmU,
-             const __grid_constant__ CUtensorMap tmW, const DsArgs a, const DsGeom g) {
-    extern __shared__ uint8_t smem_raw[];
+__device__ __forceinline__ void nl_ds_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmYmn,
+                                           const CUtensorMap& tmU, const CUtensorMap& tmW, const DsArgs& a,
+                                           const DsGeom& g, uint8_t* smem_raw) {
     __shared__ DsBars bars;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -607,6 +613,35 @@ nl_ds_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(kDsThreads, 1)
+nl_ds_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmYmn, const __grid_constant__ CUtensorMap tmU,
+             const __grid_constant__ CUtensorMap tmW, const DsArgs a, const DsGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    nl_ds_body<MODE>(tmX, tmY, tmYmn, tmU, tmW, a, g, smem_raw);
+}
+
+// The three gradient kernels of one block in ONE launch (role = blockIdx.z): each of them alone fills
+// only N/128 * B = 80 of the 148 SMs at B = 40, N = 256; as one grid of 240 CTAs the hardware scheduler
+// packs them into two waves instead of three.
+struct BwdFusedParams {
+    CUtensorMap pvX, pvY, pvW;
+    CUtensorMap dsX[2], dsY[2], dsYmn[2], dsU[2], dsW[2];
+    PvArgs pva;
+    PvGeom pvg;
+    DsArgs dsa[2];
+    DsGeom dsg;
+};
+
+__global__ void __launch_bounds__(kDsThreads, 1)
+nl_bwd_fused_kernel(const __grid_constant__ BwdFusedParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    if (blockIdx.z == 0) nl_pv_body<1>(p.pvX, p.pvY, p.pvW, p.pva, p.pvg, smem_raw);
+    else if (blockIdx.z == 1) nl_ds_body<0>(p.dsX[0], p.dsY[0], p.dsYmn[0], p.dsU[0], p.dsW[0], p.dsa[0], p.dsg, smem_raw);
+    else nl_ds_body<1>(p.dsX[1], p.dsY[1], p.dsYmn[1], p.dsU[1], p.dsW[1], p.dsa[1], p.dsg, smem_raw);
+}
+
 // E[b,i] = <dy[b,i,:], O[b,i,:]> (one warp per row); dgamma += sum E
 __global__ void __launch_bounds__(256)
 nl_rowdot_kernel(const float* __restrict__ dy, const float* __restrict__ O, float* __restrict__ E,
@@ -759,6 +794,15 @@ static int ds_launch(const char* fn, const float* X, const float* Y, const float
     return check_launch(fn);
 }
 
+static DsGeom ds_geom(int N, int d, int C) {
+    DsGeom g;
+    g.N = N; g.d = d; g.C = C; g.nkb = N / kPvKB;
+    g.nch = (C + 31) / 32;
+    g.ksteps = (d + 7) / 8;
+    g.last_ksteps = (C - 32 * (g.nch - 1) + 7) / 8;
+    return g;
+}
+
 // Full gradient on the tensor cores.  E: workspace [B,N]; dgs = {dgamma, dscale} (overwritten).
 int nonlocal_bwd_tc_launch(const float* Q, const float* K, const float* V, const float* lse, const float* O,
                            const float* dy, float* dQ, float* dK, float* dV, float* dgs, int B, int N, int d,
@@ -770,15 +814,51 @@ int nonlocal_bwd_tc_launch(const float* Q, const float* K, const float* V, const
     nl_rowdot_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dy, O, E, dgs, rows, C / 4, dy_s, o_s);
     int rc = check_launch(fn);
     if (rc) return rc;
-    rc = nonlocal_dv_tc_launch(Q, K, lse, dy, dV, B, N, d, C, q_s, k_s, dy_s, v_s, scale, gamma, st);
-    if (rc) return rc;
-    DsArgs a{};
-    a.lse = lse; a.E = E; a.scale = scale; a.gamma = gamma;
-    a.out = dQ; a.out_s = q_s; a.dscale = dgs + 1;
-    rc = ds_launch<0>(fn, Q, K, dy, V, q_s, k_s, dy_s, v_s, a, B, N, d, C, st);
-    if (rc) return rc;
-    a.out = dK; a.out_s = k_s; a.dscale = nullptr;
-    return ds_launch<1>(fn, K, Q, V, dy, k_s, q_s, v_s, dy_s, a, B, N, d, C, st);
+
+    static const bool split = [] { const char* e = getenv("DAVI_NL_BWD"); return e && strcmp(e, "split") == 0; }();
+    if (split) {                                       // three launches (A/B switch for profiling)
+        rc = nonlocal_dv_tc_launch(Q, K, lse, dy, dV, B, N, d, C, q_s, k_s, dy_s, v_s, scale, gamma, st);
+        if (rc) return rc;
+        DsArgs a{};
+        a.lse = lse; a.E = E; a.scale = scale; a.gamma = gamma;
+        a.out = dQ; a.out_s = q_s; a.dscale = dgs + 1;
+        rc = ds_launch<0>(fn, Q, K, dy, V, q_s, k_s, dy_s, v_s, a, B, N, d, C, st);
+        if (rc) return rc;
+        a.out = dK; a.out_s = k_s; a.dscale = nullptr;
+        return ds_launch<1>(fn, K, Q, V, dy, k_s, q_s, v_s, dy_s, a, B, N, d, C, st);
+    }
+
+    BwdFusedParams p{};
+    if (!pv_geom(N, d, C, true, p.pvg)) {
+        set_error("%s: shape not supported by the tensor-core kernel", fn);
+        return DAVI_EINVAL;
+    }
+    p.dsg = ds_geom(N, d, C);
+    // role 0: dV = gamma * P^T dy (rows = keys)
+    if ((rc = make_tmap_rows(&p.pvX, K, d, N, B, k_s, kPvM, false))) return rc;
+    if ((rc = make_tmap_rows(&p.pvY, Q, d, N, B, q_s, kPvKB, false))) return rc;
+    if ((rc = make_tmap_rows(&p.pvW, dy, C, N, B, dy_s, kPvKC, true))) return rc;
+    p.pva.lse_in = lse; p.pva.out = dV; p.pva.out_s = v_s; p.pva.scale = scale; p.pva.gamma = gamma;
+    // role 1: dQ (X = Q, Y = K, U = dy, W = V); role 2: dK (X = K, Y = Q, U = V, W = dy)
+    const float* X[2] = {Q, K}; const float* Y[2] = {K, Q}; const float* U[2] = {dy, V}; const float* W[2] = {V, dy};
+    const int64_t xs[2] = {q_s, k_s}, ys[2] = {k_s, q_s}, us[2] = {dy_s, v_s}, ws[2] = {v_s, dy_s};
+    float* outs[2] = {dQ, dK};
+    for (int r = 0; r < 2; ++r) {
+        if ((rc = make_tmap_rows(&p.dsX[r], X[r], d, N, B, xs[r], kPvM, false))) return rc;
+        if ((rc = make_tmap_rows(&p.dsY[r], Y[r], d, N, B, ys[r], kPvKB, false))) return rc;
+        if ((rc = make_tmap_rows(&p.dsYmn[r], Y[r], d, N, B, ys[r], kPvKB, true))) return rc;
+        if ((rc = make_tmap_rows(&p.dsU[r], U[r], C, N, B, us[r], kPvM, false))) return rc;
+        if ((rc = make_tmap_rows(&p.dsW[r], W[r], C, N, B, ws[r], kPvKB, false))) return rc;
+        p.dsa[r].lse = lse; p.dsa[r].E = E; p.dsa[r].scale = scale; p.dsa[r].gamma = gamma;
+        p.dsa[r].out = outs[r]; p.dsa[r].out_s = xs[r];
+        p.dsa[r].dscale = r == 0 ? dgs + 1 : nullptr;
+    }
+    const size_t smem_pv = 1024 + (size_t)kPvFixedBytes + (size_t)p.pvg.stages * 2 * kPvKC * p.pvg.Cp * 4 + (size_t)N * 4;
+    const size_t smem_ds = 1024 + (size_t)kDsFixedBytes + 2 * (size_t)kDsStageBytes;
+    const size_t smem = smem_pv > smem_ds ? smem_pv : smem_ds;
+    DAVI_CUDA(cudaFuncSetAttribute(nl_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nl_bwd_fused_kernel<<<dim3(N / kPvM, B, 3), kDsThreads, smem, st>>>(p);
+    return check_launch(fn);
 }
 
 }  // namespace davi
