@@ -586,7 +586,8 @@ static int dw_fwd_impl(const char* fn, const SlotPtrs& sp, const float* q, float
         }
     // v2 (bulk-copy staged, persistent) wins once a call moves >= ~130 MB (measured: n >= 10 at B*P = 10240);
     // below that the register-streaming kernel has the shorter start-up.  16 ring stages must fit 227 KB.
-    if (dw_v2_enabled() && g.C4 > 32 && g.C4 <= 80 && P % kV2TP == 0 && (int64_t)n * g.total_pix >= 10 * 10240) {
+    if (dw_v2_enabled() && g.C4 > 32 && g.C4 <= 80 && P % kV2TP == 0 && n >= 8 &&
+        (int64_t)n * g.total_pix >= 10 * 10240) {
         int dev = 0, sms = 0;
         DAVI_CUDA(cudaGetDevice(&dev));
         DAVI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
