@@ -438,50 +438,64 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
             dsc_local += ds[t] * r[t];
         }
 
-        // pass 2: writes.  lanes < d4 own one float4 column of q / dq / dK rows.
+        // pass 2: writes.  lanes < d4 own one float4 column of q / dq / dK rows.  The key rows are
+        // re-read (L1/L2 hits) in batches of kDwUnroll BEFORE the stores of the batch, so that the
+        // loads are independent instead of one dependent round trip per slot.
         const bool kcol = l < g.d4;
         float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), dqv = qv;
         if (kcol) qv = ld4(qp + 4 * l);
 #pragma unroll
         for (int t = 0; t < SPL; ++t) {
             const int jend = min(g.n, (t + 1) * G);
-            for (int j = t * G; j < jend; ++j) {
-                const int src = gbase + (j & (G - 1));
-                const float aj = __shfl_sync(gm, a[t], src);
-                const float dsj = __shfl_sync(gm, ds[t], src) * scale;
-                const bool acc = (g.acc_mask >> j) & 1u;
-                float* dvp = tg.dv[j];
-                if (dvp) {
-                    dvp += (int64_t)b * tg.v_sb[j] + (int64_t)p * tg.v_sp[j] + 4 * l;
+            for (int j0 = t * G; j0 < jend; j0 += kDwUnroll) {
+                float4 kv[kDwUnroll];
 #pragma unroll
-                    for (int it = 0; it < ITERS; ++it) {
-                        if (it < ITERS - 1 || last_ok) {
-                            float4 o;
-                            if (acc) {
-                                o = *reinterpret_cast<const float4*>(dvp + 4 * it * G);
-                                fma4(o, aj, go[it]);
-                            } else {
-                                o = make_float4(aj * go[it].x, aj * go[it].y, aj * go[it].z,
-                                                aj * go[it].w);
+                for (int u = 0; u < kDwUnroll; ++u) {
+                    const int j = j0 + u;
+                    kv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kcol && j < jend)
+                        kv[u] = ld4(tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j] + 4 * l);
+                }
+#pragma unroll
+                for (int u = 0; u < kDwUnroll; ++u) {
+                    const int j = j0 + u;
+                    if (j >= jend) break;
+                    const int src = gbase + (j & (G - 1));
+                    const float aj = __shfl_sync(gm, a[t], src);
+                    const float dsj = __shfl_sync(gm, ds[t], src) * scale;
+                    const bool acc = (g.acc_mask >> j) & 1u;
+                    float* dvp = tg.dv[j];
+                    if (dvp) {
+                        dvp += (int64_t)b * tg.v_sb[j] + (int64_t)p * tg.v_sp[j] + 4 * l;
+#pragma unroll
+                        for (int it = 0; it < ITERS; ++it) {
+                            if (it < ITERS - 1 || last_ok) {
+                                float4 o;
+                                if (acc) {
+                                    o = *reinterpret_cast<const float4*>(dvp + 4 * it * G);
+                                    fma4(o, aj, go[it]);
+                                } else {
+                                    o = make_float4(aj * go[it].x, aj * go[it].y, aj * go[it].z,
+                                                    aj * go[it].w);
+                                }
+                                st_stream4(dvp + 4 * it * G, o);
                             }
-                            st_stream4(dvp + 4 * it * G, o);
                         }
                     }
-                }
-                if (kcol) {
-                    const float4 kv = ld4(tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j] + 4 * l);
-                    fma4(dqv, dsj, kv);
-                    float* dkp = tg.dk[j];
-                    if (dkp) {
-                        dkp += (int64_t)b * tg.k_sb[j] + (int64_t)p * tg.k_sp[j] + 4 * l;
-                        float4 o;
-                        if (acc) {
-                            o = *reinterpret_cast<const float4*>(dkp);
-                            fma4(o, dsj, qv);
-                        } else {
-                            o = make_float4(dsj * qv.x, dsj * qv.y, dsj * qv.z, dsj * qv.w);
+                    if (kcol) {
+                        fma4(dqv, dsj, kv[u]);
+                        float* dkp = tg.dk[j];
+                        if (dkp) {
+                            dkp += (int64_t)b * tg.k_sb[j] + (int64_t)p * tg.k_sp[j] + 4 * l;
+                            float4 o;
+                            if (acc) {
+                                o = *reinterpret_cast<const float4*>(dkp);
+                                fma4(o, dsj, qv);
+                            } else {
+                                o = make_float4(dsj * qv.x, dsj * qv.y, dsj * qv.z, dsj * qv.w);
+                            }
+                            *reinterpret_cast<float4*>(dkp) = o;
                         }
-                        *reinterpret_cast<float4*>(dkp) = o;
                     }
                 }
             }
