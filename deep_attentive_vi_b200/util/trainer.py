@@ -63,8 +63,11 @@ def cosine_warmup_lr(step, steps_per_epoch, lr, min_lr, warmup_epochs, decay_epo
 
 
 class FlatState:
-    """Re-homes every trainable parameter (and its .grad) into flat fp32 arrays,
-    grouped by regulariser strength."""
+    """Re-homes every trainable parameter into a flat fp32 array (grouped by regulariser strength)
+    with flat gradient / Adamax-moment arrays of the same layout.  Gradients are NOT accumulated
+    into views of the flat array (that costs one tiny add_ kernel per parameter and step, ~2 600
+    launches): autograd deposits its own tensors in .grad and `gather_grads` copies them into the
+    flat array with davi_multi_copy (one launch per 64 tensors)."""
 
     def __init__(self, model, device):
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
@@ -80,6 +83,7 @@ class FlatState:
         self.U = torch.zeros(size, device=device)
         self.segments = []   # (l2, offset, length)
         self.total = total
+        self.slots = []      # (tensor that owns a .grad, flat gradient array, offset, numel, is_conv)
         off = 0
         for l2, plist in sorted(groups.items()):
             start = off
@@ -90,11 +94,11 @@ class FlatState:
                     o, i, h, w = p.shape
                     self.P[off:off + n].view(o, h, w, i).copy_(src.permute(0, 2, 3, 1))
                     p.data = self.P[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)
-                    p.grad = self.G[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)
                 else:
                     self.P[off:off + n].view(p.shape).copy_(src)
                     p.data = self.P[off:off + n].view(p.shape)
-                    p.grad = self.G[off:off + n].view(p.shape)
+                p.grad = None
+                self.slots.append((p, "G", off, n, p.dim() == 4))
                 off += pad(n)
             self.segments.append((float(l2), start, off - start))
         assert off == size
@@ -127,12 +131,41 @@ class FlatState:
             n = o * i * h * w
             wv = self.W[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)       # OHWI memory = channels_last
             wv.requires_grad_(True)
-            wv.grad = self.dW[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)
             m._w_override = wv
+            self.slots.append((wv, "dW", off, n, True))
         t64 = lambda v: torch.tensor(v, dtype=torch.int64, device=device)
         self.wn_tables = (t64(rv), t64(rg), t64(rw), torch.tensor(rc, dtype=torch.int32, device=device))
         self.wn_rows = len(rv)
         self.wn_modules = [s[0] for s in sizes]
+
+    def clear_grads(self):
+        for t, _, _, _, _ in self.slots:
+            t.grad = None
+
+    def gather_grads(self, stream):
+        """Copy every deposited gradient into its place in G (parameters) or dW (effective conv
+        kernels).  Conv gradients are stored like their weights: OHWI (channels_last) memory order."""
+        for which, flat in (("G", self.G), ("dW", getattr(self, "dW", None))):
+            ptrs, offs, sizes, keep = [], [], [], []
+            for t, w, off, n, is_conv in self.slots:
+                g = t.grad
+                if w != which or g is None:
+                    continue
+                if is_conv:
+                    if not g.permute(0, 2, 3, 1).is_contiguous():
+                        g = g.contiguous(memory_format=torch.channels_last)
+                elif not g.is_contiguous():
+                    g = g.contiguous()
+                keep.append(g)
+                ptrs.append(g.data_ptr()); offs.append(off); sizes.append(n)
+            if not ptrs:
+                continue
+            order = sorted(range(len(ptrs)), key=lambda k: -sizes[k])       # similar sizes share a launch
+            pt, pa = _lib.ptr_table([ptrs[k] for k in order])
+            ot, oa = _lib.int_table([offs[k] for k in order])
+            st_, sa = _lib.int_table([sizes[k] for k in order])
+            _lib.call("davi_multi_copy", pt, ot, st_, len(order), flat.data_ptr(), stream)
+            _lib.add_launches((len(order) + 63) // 64 - 1)
 
     def release(self):
         """Detach the model from the fused weight-norm path (it computes its kernels itself again)."""
@@ -184,10 +217,10 @@ class Trainer:
 
     def forward_backward(self, x, eps=None, noise=None):
         st = self.state
-        st.G.zero_()
+        st.G.zero_()                                                 # parameters that get no gradient this step
+        st.clear_grads()
         stream = torch.cuda.current_stream().cuda_stream
         if st.wn_rows:                                               # all conv kernels: v, log_g -> W
-            st.dW.zero_()
             rv, rg, rw, rc = st.wn_tables
             _lib.call("davi_weight_norm_fwd", st.P.data_ptr(), st.W.data_ptr(), rv.data_ptr(), rg.data_ptr(),
                       rw.data_ptr(), rc.data_ptr(), st.wn_rows, stream)
@@ -195,6 +228,7 @@ class Trainer:
         global_batch = x.shape[0] * self.world                       # tr.py:174
         loss = (nll.sum() + self.beta_dev * kl.sum()) * (1.0 / global_batch)
         loss.backward()
+        st.gather_grads(stream)                                      # per-tensor gradients -> flat G / dW
         if st.wn_rows:                                               # dW -> grads of v and log_g
             _lib.call("davi_weight_norm_bwd", st.P.data_ptr(), st.dW.data_ptr(), st.G.data_ptr(), rv.data_ptr(),
                       rg.data_ptr(), rw.data_ptr(), rc.data_ptr(), st.wn_rows, stream)

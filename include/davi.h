@@ -291,6 +291,14 @@ size_t davi_colsum_workspace_bytes(int64_t rows, int C);
 int davi_colsum(const float* x, float* out, int64_t rows, int C, int64_t x_s,
                 void* workspace, size_t workspace_bytes, davi_stream_t stream);
 
+/* 8(f4)  dst[dst_offsets[i] : dst_offsets[i] + sizes[i]] = srcs[i][0 : sizes[i]] for `count`
+ * device tensors, 64 tensors per launch.  srcs / dst_offsets / sizes are HOST arrays
+ * (copied into the launch arguments).  Gathers the per-variable gradients into the flat
+ * gradient array of the data-parallel step (reference: Keras' per-variable gradient
+ * aggregation under MirroredStrategy, util/trainer.py:160-187). */
+int davi_multi_copy(const float* const* srcs, const int64_t* dst_offsets, const int64_t* sizes,
+                    int count, float* dst, davi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
