@@ -277,3 +277,57 @@ def test_conv_bias_gradient_path_matches_autograd(cuda):
     assert torch.allclose(y1, y2)
     for a, c in zip(g1, g2):
         assert ((a - c).abs().max() / c.abs().max()).item() < 1e-5
+
+
+def test_shared_slot_lazy_gradient_gather_equals_autograd_sum(cuda):
+    """Three consumers attend to the same context tensors: the SharedSlot path (later consumers
+    accumulate into one buffer from their backward kernels, the earliest one returns it) must give
+    the gradients autograd gets by summing per-consumer slice gradients."""
+    from deep_attentive_vi_b200 import ops
+    torch.manual_seed(11)
+    B, H, W, d, C = 2, 8, 8, 20, 36
+    ctx = [torch.randn(B, H, W, C + d, device=cuda, requires_grad=True) for _ in range(3)]
+    own_k = [torch.randn(B, H, W, d, device=cuda, requires_grad=True) for _ in range(3)]
+    own_v = [torch.randn(B, H, W, C, device=cuda, requires_grad=True) for _ in range(3)]
+    qs = [torch.randn(B, H, W, d, device=cuda, requires_grad=True) for _ in range(3)]
+    gos = [torch.randn(B, H, W, C, device=cuda) for _ in range(3)]
+    leaves = ctx + own_k + own_v + qs
+
+    def run(shared):
+        loss = 0.0
+        if shared:
+            base = [t * 1.0 for t in ctx]                     # non-leaf, like the model's contexts
+            sh = [ops.SharedSlot(t, C) for t in base]
+        for layer in range(3):                                 # consumer `layer` sees contexts 0..layer
+            if shared:
+                # context k is first consumed by layer k ("own"); later layers accumulate
+                slots = [("own", sh[k]) if k == layer else ("acc", sh[k]) for k in range(layer + 1)]
+            else:
+                slots = [("kv", ctx[k][..., C:], ctx[k][..., :C]) for k in range(layer + 1)]
+            slots.append(("kv", own_k[layer], own_v[layer]))
+            out = ops.dw_attn_ctx(qs[layer], slots)
+            loss = loss + (out * gos[layer]).sum()
+        return torch.autograd.grad(loss, leaves)
+
+    want = run(False)
+    got = run(True)
+    for a, b in zip(got, want):
+        assert ((a - b).abs().max() / b.abs().max()).item() < 1e-5
+
+
+@pytest.mark.parametrize("B,n,H,d,C", [(1, 32, 4, 8, 8), (1, 1, 2, 4, 4), (3, 7, 6, 20, 276), (2, 17, 16, 32, 288)])
+def test_dw_attn_edge_shapes(cuda, B, n, H, d, C):
+    """maximum slot count, single slot, pixel counts that are not tile multiples, ragged last column block"""
+    from deep_attentive_vi_b200 import ops
+    torch.manual_seed(B * 100 + n)
+    q, k, v = torch.randn(B, H, H, d), torch.randn(B, n, H, H, d), torch.randn(B, n, H, H, C)
+    go = torch.randn(B, H, H, C)
+    ins = [t.to(cuda).requires_grad_() for t in (q, k, v)]
+    out = ops.dw_attn(*ins)
+    out.backward(go.to(cuda))
+    rins = [t.double().requires_grad_() for t in (q, k, v)]
+    want = ref.depthwise_attention_apply(*rins)
+    want.backward(go.double())
+    assert rel_err(out, want) < 1e-6
+    for g, w in zip(ins, rins):
+        assert rel_err(g.grad, w.grad) < 1e-5
