@@ -152,52 +152,60 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 
 def dw_roofline(batch, device):
+    """Achieved bandwidth of the model's 31 forward + 31 backward depth-wise attention launches.
+
+    Timing: for every call shape the kernel is launched back to back on ROTATING operand sets whose
+    total footprint exceeds 3x the 126 MB L2 (so every launch reads cold inputs: "inputs larger than
+    L2"), all launches of a shape between ONE pair of CUDA events on the launching stream; the
+    per-launch time is the mean.  (Timing single launches between their own event pair adds the
+    ~2 us event granularity to kernels that run 13-45 us.)"""
     import torch
     from deep_attentive_vi_b200 import _lib
     L, d, HW, P = 16, 20, 16, 256
     stream = torch.cuda.current_stream().cuda_stream
-    # L2 flush before every timed launch: write 256 MB, then READ another 256 MB so that the cache is left
-    # full of clean lines (a write-only flush makes the timed kernel pay the write-back of the flush itself)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
-    flush_rd = torch.zeros(256 * 1024 * 1024 // 4, device=device)
     calls = [("dec", i, 276) for i in range(1, L)] + [("enc", L + 1 - i, 256) for i in range(L)]
-    nmax = L + 1
-    Cmax = 276
-    K = torch.randn(batch, nmax, HW, HW, d, device=device)
-    V = torch.randn(batch, nmax, HW, HW, Cmax, device=device)
-    q = torch.randn(batch, HW, HW, d, device=device)
-    go = torch.randn(batch, HW, HW, Cmax, device=device)
-    out = torch.empty(batch, HW, HW, Cmax, device=device)
-    dK, dV, dq = torch.empty_like(K), torch.empty_like(V), torch.empty_like(q)
+    footprint = 3 * 126e6
     tot_b = tot_t = 0.0
     per_call = []
     for kind, n, C in calls:
-        k, v = K[:, :n].contiguous(), V[:, :n, ..., :C].contiguous()
-        dk, dv = dK[:, :n].contiguous(), dV[:, :n, ..., :C].contiguous()
-        o_, g_ = out[..., :C].contiguous(), go[..., :C].contiguous()
         fb = 4 * batch * P * (n * (d + C) + d + C)
         bb = 4 * batch * P * (2 * n * (d + C) + 2 * d + C)
-        fa = (q.data_ptr(), k.data_ptr(), v.data_ptr(), o_.data_ptr(), 0, batch, n, P, d, C,
-              d, n * P * d, P * d, d, n * P * C, P * C, C, C, 0, stream)
-        ba = (q.data_ptr(), k.data_ptr(), v.data_ptr(), g_.data_ptr(), dq.data_ptr(), dk.data_ptr(),
-              dv.data_ptr(), 0, batch, n, P, d, C, d, n * P * d, P * d, d, n * P * C, P * C, C, C, 0, stream)
-        for name, a, nbytes in (("davi_dw_attn_fwd", fa, fb), ("davi_dw_attn_bwd", ba, bb)):
+        sets = max(2, min(24, int(footprint // fb) + 1))
+        mk = lambda *shape: [torch.randn(*shape, device=device) for _ in range(sets)]
+        q, K, V, go = mk(batch, P, d), mk(batch, n, P, d), mk(batch, n, P, C), mk(batch, P, C)
+        out = [torch.empty(batch, P, C, device=device) for _ in range(sets)]
+        dq = [torch.empty_like(t) for t in q]
+        dK = [torch.empty(batch, n, P, d, device=device) for _ in range(min(sets, 4))]
+        dV = [torch.empty(batch, n, P, C, device=device) for _ in range(min(sets, 4))]
+
+        def fwd(s):
+            _lib.call("davi_dw_attn_fwd", q[s].data_ptr(), K[s].data_ptr(), V[s].data_ptr(), out[s].data_ptr(), 0,
+                      batch, n, P, d, C, d, n * P * d, P * d, d, n * P * C, P * C, C, C, 0, stream)
+
+        def bwd(s):
+            g = s % len(dK)
+            _lib.call("davi_dw_attn_bwd", q[s].data_ptr(), K[s].data_ptr(), V[s].data_ptr(), go[s].data_ptr(),
+                      dq[s].data_ptr(), dK[g].data_ptr(), dV[g].data_ptr(), 0, batch, n, P, d, C,
+                      d, n * P * d, P * d, d, n * P * C, P * C, C, C, 0, stream)
+
+        for name, fn, nbytes in (("fwd", fwd, fb), ("bwd", bwd, bb)):
+            for s in range(sets):                       # warm-up round (also touches every set once)
+                fn(s)
             ts = []
-            for rep in range(4):
-                flush.fill_(0.0)
-                flush_rd.sum()
+            for rep in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                _lib.call(name, *a)
+                for s in range(sets):
+                    fn(s)
                 e1.record()
                 e1.synchronize()
-                if rep:
-                    ts.append(e0.elapsed_time(e1))
-            t = sorted(ts)[len(ts) // 2]
+                ts.append(e0.elapsed_time(e1) / sets)
+            t = sorted(ts)[1]
             tot_b += nbytes
             tot_t += t
-            per_call.append({"k": name[-3:], "n": n, "C": C, "us": round(t * 1e3, 1),
+            per_call.append({"k": name, "n": n, "C": C, "sets": sets, "us": round(t * 1e3, 1),
                              "GBs": round(nbytes / t / 1e6)})
+        del q, K, V, go, out, dq, dK, dV
     return tot_b, tot_t, per_call
 
 
@@ -289,8 +297,8 @@ def run_davi(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "params": nparams,
                    "parallelism": f"dp{world}", "cuda_graph": not args.eager, "convs": "cuDNN fp32" if args.fp32_convs else "cuDNN tf32",
-                   "l2": "inputs (2 GB activations per step) exceed L2; dw-attention roofline calls are "
-                         "timed after an explicit L2 flush (256 MB written, then 256 MB read)"},
+                   "l2": "inputs (2 GB activations per step) exceed L2; dw-attention roofline launches rotate over "
+                         "operand sets with a total footprint > 3x L2 (every launch reads cold inputs)"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 32 * 3 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss")},
         "gpu_launches": launches,

@@ -92,10 +92,13 @@ __device__ __forceinline__ void dw_scores(const SlotTable& tb, const DwGeom& g, 
     for (int t = 0; t < SPL; ++t) a[t] *= inv;
 }
 
-template <int G, int ITERS>
-__global__ void __launch_bounds__(kDwThreads)
-dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __restrict__ out,
-                   float* __restrict__ attn, const DwGeom g) {
+// UNROLL = slots whose value rows are in flight together.  Calls with few slots (n <= 4: the first
+// layers, 24-60 MB) are bound by launch + wave count, not by bytes in flight: UNROLL 1 / 2 halves the
+// registers (128 -> ~85 / ~100) so that the whole grid is resident in one or two waves instead of three.
+template <int G, int ITERS, int UNROLL>
+__device__ __forceinline__ void dw_attn_fwd_body(const SlotPtrs& sp, const float* __restrict__ q,
+                                                 float* __restrict__ out, float* __restrict__ attn,
+                                                 const DwGeom& g) {
     constexpr int SPL = DAVI_MAX_SLOTS / G;
     __shared__ SlotTable tb;
     if (threadIdx.x < DAVI_MAX_SLOTS) {
@@ -133,10 +136,10 @@ dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __rest
     for (int t = 0; t < SPL; ++t) {
         const int jend = min(g.n, (t + 1) * G);
         int j = t * G;
-        for (; j + kDwUnroll <= jend; j += kDwUnroll) {
-            float4 v[kDwUnroll][ITERS];
+        for (; j + UNROLL <= jend; j += UNROLL) {
+            float4 v[UNROLL][ITERS];
 #pragma unroll
-            for (int u = 0; u < kDwUnroll; ++u) {
+            for (int u = 0; u < UNROLL; ++u) {
                 const float* vp = vrow(j + u);
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
@@ -145,7 +148,7 @@ dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __rest
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kDwUnroll; ++u) {
+            for (int u = 0; u < UNROLL; ++u) {
                 const float aj = __shfl_sync(gm, a[t], gbase + ((j + u) & (G - 1)));
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) fma4(acc[it], aj, v[u][it]);
@@ -169,6 +172,19 @@ dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __rest
 #pragma unroll
     for (int it = 0; it < ITERS; ++it)
         if (it < ITERS - 1 || last_ok) st_stream4(op + 4 * it * G, acc[it]);
+}
+
+template <int G, int ITERS>
+__global__ void __launch_bounds__(kDwThreads)
+dw_attn_fwd_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __restrict__ out,
+                   float* __restrict__ attn, const DwGeom g) {
+    dw_attn_fwd_body<G, ITERS, 4>(sp, q, out, attn, g);
+}
+template <int G, int ITERS, int UNROLL>
+__global__ void __launch_bounds__(kDwThreads, UNROLL == 1 ? 6 : 5)
+dw_attn_fwd_small_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __restrict__ out,
+                         float* __restrict__ attn, const DwGeom g) {
+    dw_attn_fwd_body<G, ITERS, UNROLL>(sp, q, out, attn, g);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -343,11 +359,11 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
 // Backward.  Per pixel: recompute a; pass 1 streams V once for da_j = <V_j, g>;
 // ds_j = a_j (da_j - sum_k a_k da_k); pass 2 only writes: dV_j = a_j g,
 // dK_j = scale ds_j q, dq = scale sum_j ds_j K_j (K rows re-read from L1/L2).
-template <int G, int ITERS>
-__global__ void __launch_bounds__(kDwThreads)
-dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __restrict__ q,
-                   const float* __restrict__ dout, float* __restrict__ dq,
-                   float* __restrict__ dscale, const DwGeom g) {
+template <int G, int ITERS, int UNROLL>
+__device__ __forceinline__ void dw_attn_bwd_body(const SlotPtrs& sp, const SlotGradPtrs& gp,
+                                                 const float* __restrict__ q, const float* __restrict__ dout,
+                                                 float* __restrict__ dq, float* __restrict__ dscale,
+                                                 const DwGeom& g) {
     constexpr int SPL = DAVI_MAX_SLOTS / G;
     __shared__ SlotTable tb;
     __shared__ SlotGradPtrs tg;
@@ -396,10 +412,10 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
             da[t] = 0.f;
             const int jend = min(g.n, (t + 1) * G);
             int j = t * G;
-            for (; j + kDwUnroll <= jend; j += kDwUnroll) {
-                float4 v[kDwUnroll][ITERS];
+            for (; j + UNROLL <= jend; j += UNROLL) {
+                float4 v[UNROLL][ITERS];
 #pragma unroll
-                for (int u = 0; u < kDwUnroll; ++u) {
+                for (int u = 0; u < UNROLL; ++u) {
                     const float* vp = vrow(j + u);
 #pragma unroll
                     for (int it = 0; it < ITERS; ++it) {
@@ -408,7 +424,7 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < kDwUnroll; ++u) {
+                for (int u = 0; u < UNROLL; ++u) {
                     float part = 0.f;
 #pragma unroll
                     for (int it = 0; it < ITERS; ++it) part += dot4(v[u][it], go[it]);
@@ -439,7 +455,7 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
         }
 
         // pass 2: writes.  lanes < d4 own one float4 column of q / dq / dK rows.  The key rows are
-        // re-read (L1/L2 hits) in batches of kDwUnroll BEFORE the stores of the batch, so that the
+        // re-read (L1/L2 hits) in batches of UNROLL BEFORE the stores of the batch, so that the
         // loads are independent instead of one dependent round trip per slot.
         const bool kcol = l < g.d4;
         float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), dqv = qv;
@@ -447,17 +463,17 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
 #pragma unroll
         for (int t = 0; t < SPL; ++t) {
             const int jend = min(g.n, (t + 1) * G);
-            for (int j0 = t * G; j0 < jend; j0 += kDwUnroll) {
-                float4 kv[kDwUnroll];
+            for (int j0 = t * G; j0 < jend; j0 += UNROLL) {
+                float4 kv[UNROLL];
 #pragma unroll
-                for (int u = 0; u < kDwUnroll; ++u) {
+                for (int u = 0; u < UNROLL; ++u) {
                     const int j = j0 + u;
                     kv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (kcol && j < jend)
                         kv[u] = ld4(tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j] + 4 * l);
                 }
 #pragma unroll
-                for (int u = 0; u < kDwUnroll; ++u) {
+                for (int u = 0; u < UNROLL; ++u) {
                     const int j = j0 + u;
                     if (j >= jend) break;
                     const int src = gbase + (j & (G - 1));
@@ -509,6 +525,21 @@ dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __rest
     }
 }
 
+template <int G, int ITERS>
+__global__ void __launch_bounds__(kDwThreads)
+dw_attn_bwd_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __restrict__ q,
+                   const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dscale,
+                   const DwGeom g) {
+    dw_attn_bwd_body<G, ITERS, 4>(sp, gp, q, dout, dq, dscale, g);
+}
+template <int G, int ITERS, int UNROLL>
+__global__ void __launch_bounds__(kDwThreads, UNROLL == 1 ? 6 : 5)
+dw_attn_bwd_small_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __restrict__ q,
+                         const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dscale,
+                         const DwGeom g) {
+    dw_attn_bwd_body<G, ITERS, UNROLL>(sp, gp, q, dout, dq, dscale, g);
+}
+
 // ---- host-side dispatch ----------------------------------------------------
 
 static int dw_validate(const char* fn, int B, int n, int P, int d, int C, const DwGeom& g) {
@@ -543,14 +574,18 @@ static void launch_fwd(const SlotPtrs& sp, const float* q, float* out, float* at
                        cudaStream_t st) {
     const int64_t threads = (int64_t)g.total_pix * G;
     const int grid = (int)((threads + kDwThreads - 1) / kDwThreads);
-    dw_attn_fwd_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
+    if (g.n <= 2) dw_attn_fwd_small_kernel<G, ITERS, 1><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
+    else if (g.n <= 5) dw_attn_fwd_small_kernel<G, ITERS, 2><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
+    else dw_attn_fwd_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
 }
 template <int G, int ITERS>
 static void launch_bwd(const SlotPtrs& sp, const SlotGradPtrs& gp, const float* q, const float* dout,
                        float* dq, float* dscale, const DwGeom& g, cudaStream_t st) {
     const int64_t threads = (int64_t)g.total_pix * G;
     const int grid = (int)((threads + kDwThreads - 1) / kDwThreads);
-    dw_attn_bwd_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
+    if (g.n <= 2) dw_attn_bwd_small_kernel<G, ITERS, 1><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
+    else if (g.n <= 5) dw_attn_bwd_small_kernel<G, ITERS, 2><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
+    else dw_attn_bwd_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
 }
 
 #define DW_DISPATCH(LAUNCH, ...)                                   \
