@@ -30,6 +30,8 @@ SIGNATURES = {
     "davi_ln_gelu_fwd": (_i, [_f, _f, _f, _f, _l, _i, _l, _l, _r, _i, _s]),
     "davi_ln_gelu_bwd_workspace_bytes": (_z, [_l, _i]),
     "davi_ln_gelu_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _l, _i, _l, _l, _l, _r, _i, _f, _z, _s]),
+    "davi_ln_gelu_res_fwd": (_i, [_f, _f, _f, _f, _f, _f, _l, _i, _l, _l, _l, _r, _s]),
+    "davi_ln_gelu_res_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _l, _l, _l, _r, _f, _z, _s]),
     "davi_nonlocal_attn_fwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _f, _f, _s]),
     "davi_nonlocal_attn_bwd_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "davi_nonlocal_attn_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _l, _l, _l, _l, _l, _f, _f, _f, _z, _s]),
@@ -87,7 +89,7 @@ def check(rc, what):
 
 # kernels launched by one successful call of each entry point (bench.py's
 # `gpu_launches` claim is the sum over the timed region)
-KERNELS_PER_CALL = {"davi_ln_gelu_bwd": 2, "davi_nonlocal_attn_bwd": 4, "davi_colsum": 2}
+KERNELS_PER_CALL = {"davi_ln_gelu_bwd": 2, "davi_ln_gelu_res_bwd": 2, "davi_nonlocal_attn_bwd": 4, "davi_colsum": 2}
 _launches = 0
 
 

@@ -151,9 +151,11 @@ class VariationalLayer(nn.Module):
                 last_values = ops.layer_norm(last_values, self.attn_ln_gamma, self.attn_ln_beta)      # vl.py:396-401
             slots.append(("kv", last_key, last_values))
             att = self._decoder_attention.apply_ctx(query, slots)                           # vl.py:403-406
-            if self._dec_ln:
-                att = ops.ln_gelu_residual(att, self.attn_ln2_gamma, self.attn_ln2_beta)    # vl.py:408-409
-            prior_condition = new_context + self._gamma * att                               # vl.py:412
+            if self._dec_ln:                                                                # vl.py:408-412, fused
+                prior_condition = ops.ln_gelu_res(att, self.attn_ln2_gamma, self.attn_ln2_beta, new_context,
+                                                  self._gamma)
+            else:
+                prior_condition = new_context + self._gamma * att                           # vl.py:412
         else:
             prior_condition = new_context
         return new_context, prior_condition, key, enc_query
@@ -184,9 +186,11 @@ class VariationalLayer(nn.Module):
                 cond, key0 = cond[..., :f], cond[..., f:]                                   # vl.py:483-494
             att = self._encoder_attention.apply_ctx(enc_query, [("kv", key0, cond)] + list(condition[1:]))  # vl.py:496-499
             if self._enc_ln:
-                att = ops.ln_gelu_residual(att, self.enc_ln_gamma, self.enc_ln_beta)        # vl.py:502
                 cond = ops.ln_gelu_residual(cond, self.cond_ln_gamma, self.cond_ln_beta)    # vl.py:503
-            cond = cond + self._encoder_gamma * att                                         # vl.py:505
+                cond = ops.ln_gelu_res(att, self.enc_ln_gamma, self.enc_ln_beta, cond,
+                                       self._encoder_gamma)                                 # vl.py:502,505 fused
+            else:
+                cond = cond + self._encoder_gamma * att                                     # vl.py:505
             cond = torch.cat([cond, key0], dim=-1)                                          # vl.py:507
         n_post, n_prior = noise if noise is not None else (None, None)
         prior = self._prior_network if (not_first and self._residual) else None

@@ -289,6 +289,46 @@ class _LnGelu(torch.autograd.Function):
         return dx, dg, db, None, None
 
 
+class _LnGeluRes(torch.autograd.Function):
+    """y = base + res_gamma * (x + gelu(LN(x)))  (vl.py:408-412, 501-505) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, base, res_gamma, eps):
+        _require_cuda(x, gamma, beta, base, res_gamma)
+        C = x.shape[-1]
+        xr, x_s = _rows(x)
+        br, b_s = _rows(base)
+        rows = xr.numel() // C
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        g, b = gamma.contiguous(), beta.contiguous()
+        rg, rg_ptr = _scalar_ptr(res_gamma, x)
+        _lib_call("davi_ln_gelu_res_fwd", _p(xr), _p(g), _p(b), _p(br), rg_ptr, _p(y), rows, C, x_s, b_s, C, eps,
+                  _stream())
+        ctx.save_for_backward(xr, g, b, rg)
+        ctx.cfg = (rows, C, x_s, eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, g, b, rg = ctx.saved_tensors
+        rows, C, x_s, eps = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty(dy.shape, device=dy.device, dtype=torch.float32)
+        dg, db = torch.empty_like(g), torch.empty_like(b)
+        drg = torch.empty((), device=dy.device, dtype=torch.float32)
+        wsb = _lib.load().davi_ln_gelu_bwd_workspace_bytes(rows, C)
+        ws = torch.empty(wsb // 4, device=dy.device, dtype=torch.float32)
+        _lib_call("davi_ln_gelu_res_bwd", _p(xr), _p(g), _p(b), _p(rg), _p(dy), _p(dx), _p(dg), _p(db), _p(drg),
+                  rows, C, x_s, C, C, eps, _p(ws), wsb, _stream())
+        return dx, dg, db, dy, drg, None
+
+
+def ln_gelu_res(x, gamma, beta, base, res_gamma, eps=1e-5):
+    """base + res_gamma * (x + gelu(LN(x))): the post-attention glue of both attentions
+    (reference vl.py:408-412 and 501-505) as ONE kernel forward and one backward."""
+    return _LnGeluRes.apply(x, gamma, beta, base, res_gamma, eps)
+
+
 def layer_norm(x, gamma, beta, eps=1e-5):
     """LayerNormalization over the last axis (reference vl.py:399, vae.py:347-348)."""
     return _LnGelu.apply(x, gamma, beta, eps, 0)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DAVI_VERSION 102          /* major*100 + minor */
+#define DAVI_VERSION 103          /* major*100 + minor */
 #define DAVI_MAX_SLOTS 32         /* max stacked layers n of the depth-wise attention */
 
 #define DAVI_OK 0
@@ -140,6 +140,22 @@ int davi_ln_gelu_bwd(const float* x, const float* gamma, const float* beta,
                      int64_t rows, int C, int64_t x_s, int64_t dy_s, int64_t dx_s,
                      float eps, int mode, void* workspace, size_t workspace_bytes,
                      davi_stream_t stream);
+
+/* The same glue with the gamma-residual of model/variational_layer.py:408-412 / 501-505 folded in:
+ *     y = base + res_gamma * (x + gelu(LN(x)))
+ * base, y [rows,C] (row strides base_s, y_s); res_gamma: DEVICE scalar (the zero-initialised
+ * `gamma` / `enc_gamma` weights, vl.py:226-230,241-245).  The backward returns dx, the LN
+ * parameter gradients and d res_gamma (ONE float, overwritten); d base == dy is left to the caller. */
+int davi_ln_gelu_res_fwd(const float* x, const float* gamma, const float* beta, const float* base,
+                         const float* res_gamma, float* y,
+                         int64_t rows, int C, int64_t x_s, int64_t base_s, int64_t y_s,
+                         float eps, davi_stream_t stream);
+int davi_ln_gelu_res_bwd(const float* x, const float* gamma, const float* beta,
+                         const float* res_gamma, const float* dy,
+                         float* dx, float* dgamma, float* dbeta, float* dres_gamma,
+                         int64_t rows, int C, int64_t x_s, int64_t dy_s, int64_t dx_s,
+                         float eps, void* workspace, size_t workspace_bytes,
+                         davi_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * R4  Nonlocal spatial self-attention core.

@@ -331,3 +331,23 @@ def test_dw_attn_edge_shapes(cuda, B, n, H, d, C):
     assert rel_err(out, want) < 1e-6
     for g, w in zip(ins, rins):
         assert rel_err(g.grad, w.grad) < 1e-5
+
+
+def test_ln_gelu_residual_fused_with_gamma_matches_oracle(cuda):
+    """y = base + g * (x + gelu(LN(x))) (vl.py:408-412 / 501-505), forward and every gradient vs fp64."""
+    from deep_attentive_vi_b200 import ops
+    torch.manual_seed(21)
+    B, H, C = 3, 16, 276
+    x, base = torch.randn(B, H, H, C), torch.randn(B, H, H, C)
+    lg, lb = 1 + 0.2 * torch.randn(C), 0.2 * torch.randn(C)
+    rg = torch.tensor(-0.7)
+    go = torch.randn(B, H, H, C)
+    ins = [t.to(cuda).requires_grad_() for t in (x, lg, lb, base, rg)]
+    y = ops.ln_gelu_res(*ins)
+    y.backward(go.to(cuda))
+    r = [t.double().requires_grad_() for t in (x, lg, lb, base, rg)]
+    want = r[3] + r[4] * (r[0] + ref.gelu(ref.layer_norm(r[0], r[1], r[2])))
+    want.backward(go.double())
+    assert rel_err(y, want) < 1e-6
+    for got, w, name in zip(ins, r, "x ln_gamma ln_beta base res_gamma".split()):
+        assert rel_err(got.grad, w.grad) < 2e-5, name
