@@ -10,8 +10,9 @@ Outputs (committed):
                          GaussianDiag (bounds, residual, KL, log-probs), DiscretizedLogisticMixture
                          and Bernoulli log_prob
   ref_small_cifar.npz    whole-model [nll, kl, nelbo] of DeepVAE.call for a 4-layer CIFAR-like
-  ref_small_omniglot.npz config / a 3-layer OMNIGLOT-like config: weights (by reference attribute
-                         path), input batch, every random draw in call order, outputs
+  ref_small_omniglot.npz config / a 3-layer OMNIGLOT-like config / a 3-layer NVAE-like config without
+  ref_small_nvae.npz     attention: weights (by reference attribute path), input batch, every random
+                         draw in call order, outputs
 What this pins: the reference's Python logic (reshape scrambles, channel maps, stack/split order,
 LN placement, residual parametrisation, loss assembly).  What it assumes: the TF/TFP/tfa kernels
 behave as tf_shim.py restates them (documented semantics of the pinned versions).
@@ -212,3 +213,4 @@ if __name__ == "__main__":
     ops_case("ref_ops.npz")
     model_case(helpers.SMALL_CIFAR, "ref_small_cifar.npz", batch=2, seed=11)
     model_case(helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz", batch=2, seed=12)
+    model_case(helpers.SMALL_NVAE, "ref_small_nvae.npz", batch=2, seed=13)      # no attention, no nonlocal

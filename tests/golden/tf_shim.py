@@ -181,6 +181,8 @@ def reduce_logsumexp(x, axis=None, keepdims=False, name=None):
 
 
 def concat(values, axis, name=None):
+    if isinstance(values, torch.Tensor):          # array_ops.concat: a single tensor is wrapped in a list -> identity
+        return _t(values)
     return torch.cat([_t(v) for v in values], dim=int(axis)).as_subclass(T)
 
 

@@ -31,6 +31,19 @@ SMALL_OMNIGLOT = dict(
 )
 
 
+# NVAE-like baseline of the reference README (no depth-wise attention, no nonlocal blocks)
+SMALL_NVAE = dict(
+    dataset="cifar10",
+    hparams="layer_latent_shape=[16,16,4],num_layers=3,data_distribution=discretized_logistic_mixture",
+    decoder_hparams="scale=[0,0],num_blocks=2,num_filters=8",
+    encoder_hparams="scale=[0,0],num_blocks=2,num_filters=8",
+    preproc_encoder_hparams="scale=[0,-2],num_blocks=2,num_filters=8",
+    postproc_decoder_hparams="scale=[2,0],num_blocks=2,num_filters=8",
+    posterior_hparams="log_scale_upper_bound=5,log_scale_low_bound=-5",
+    prior_hparams="log_scale_upper_bound=5,log_scale_low_bound=-5.0",
+)
+
+
 def oracle_cfg(kw):
     """DeepVAE constructor kwargs (HParams objects) -> the oracle's plain dict."""
     hp, info = kw["hparams"], kw["image_info"]

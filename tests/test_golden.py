@@ -55,7 +55,8 @@ def test_bernoulli_log_prob_matches_reference_code(ops_fix):
 
 
 @pytest.mark.parametrize("flags,fname", [(helpers.SMALL_CIFAR, "ref_small_cifar.npz"),
-                                         (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz")])
+                                         (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz"),
+                                         (helpers.SMALL_NVAE, "ref_small_nvae.npz")])
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_whole_model_elbo_matches_reference_code(flags, fname, mode):
     """[nll, sum kl, nelbo] of the reference's DeepVAE.call on the reference's weights and draws."""

@@ -15,6 +15,25 @@ def _fp32_exact():
     torch.backends.cuda.matmul.allow_tf32 = False
 
 
+def test_model_without_attention_matches_oracle(cuda):
+    """The reference's NVAE baseline configuration (README.md:105): no depth-wise attention, no nonlocal
+    blocks -- the tensor (not slot-list) branches of encode / call_decoder."""
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    _fp32_exact()
+    kw = parse_flags(**helpers.SMALL_NVAE)
+    torch.manual_seed(0)
+    m = DeepVAE(**kw)
+    B = 3
+    x = helpers.synthetic_images(kw, B)
+    eps, noise = m.draw_noise(B, "cpu", generator=torch.Generator().manual_seed(1), training=True)
+    nll_o, kl_o, _ = OracleVAE(helpers.oracle_cfg(kw), m.state_dict()).forward(x, eps, True, noise)
+    m = m.to(cuda)
+    with torch.no_grad():
+        nll, kl, _ = m(x.to(cuda), True, [e.to(cuda) for e in eps], None)
+    rel = lambda a, b: ((a.double().cpu() - b).abs() / b.abs()).max().item()
+    assert rel(nll, nll_o) < 1e-4 and rel(kl, kl_o) < 1e-4
+
+
 @pytest.mark.parametrize("flags", [helpers.SMALL_CIFAR, helpers.SMALL_OMNIGLOT], ids=["cifar", "omniglot"])
 def test_elbo_and_gradients_match_oracle(cuda, flags):
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
@@ -73,7 +92,8 @@ def test_importance_sampled_chunk_matches_oracle(cuda):
 
 
 @pytest.mark.parametrize("flags,fname", [(helpers.SMALL_CIFAR, "ref_small_cifar.npz"),
-                                         (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz")], ids=["cifar", "omniglot"])
+                                         (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz"),
+                                         (helpers.SMALL_NVAE, "ref_small_nvae.npz")], ids=["cifar", "omniglot", "nvae"])
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_elbo_matches_reference_code_golden(cuda, flags, fname, mode):
     """The CUDA path against the committed output of the reference's OWN DeepVAE.call (executed in
