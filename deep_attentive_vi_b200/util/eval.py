@@ -35,16 +35,48 @@ def combine_partial_logsumexp(partials, num_samples):
     return torch.logsumexp(partials, dim=0) - math.log(num_samples)
 
 
+class GraphedChunks:
+    """CUDA graphs of DeepVAE.infer_worker_body, one per chunk size: a chunk is ~5 000 kernel launches,
+    so the eager loop of the reference (vae.py:515-535, a serial tf.while_loop) is host-bound; the graph
+    replays it with one host call.  The random draws come from the default CUDA generator, which
+    torch.cuda.graph registers, so every replay uses fresh importance samples."""
+
+    def __init__(self, model, x):
+        self.model = model
+        self.x = x.clone()
+        self.graphs = {}
+        self.side = torch.cuda.Stream(device=x.device)
+
+    @torch.no_grad()
+    def __call__(self, x, n):
+        self.x.copy_(x)
+        if n not in self.graphs:
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                self.model.infer_worker_body(self.x, n)               # warm-up (cuDNN algorithm selection)
+            cur.wait_stream(self.side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.side):
+                out = self.model.infer_worker_body(self.x, n)
+            self.graphs[n] = (g, out)
+        g, out = self.graphs[n]
+        g.replay()
+        return out.clone()
+
+
 @torch.no_grad()
-def importance_log_likelihood(model, x, num_samples, max_chunk=25, world=1, rank=0, group=None):
+def importance_log_likelihood(model, x, num_samples, max_chunk=25, world=1, rank=0, group=None, chunks=None):
     """log p_hat(x) [B] with K = num_samples importance samples, this rank
-    computing its shard in chunks of at most `max_chunk` samples."""
+    computing its shard in chunks of at most `max_chunk` samples.  `chunks`: a GraphedChunks
+    instance to replay CUDA graphs instead of launching every chunk eagerly."""
     lo, hi = shard_samples(num_samples, world, rank)
     parts = []
     k = lo
     while k < hi:
         n = min(max_chunk, hi - k)
-        parts.append(model.infer_worker_body(x, n))
+        parts.append(chunks(x, n) if chunks is not None else model.infer_worker_body(x, n))
         k += n
     local = torch.logsumexp(torch.stack(parts, 0), dim=0)            # [B]
     if world > 1:

@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deep_attentive_vi_b200.model import CIFAR10_16L, DeepVAE, parse_flags  # noqa: E402
-from deep_attentive_vi_b200.util.eval import importance_log_likelihood  # noqa: E402
+from deep_attentive_vi_b200.util.eval import GraphedChunks, importance_log_likelihood  # noqa: E402
 
 
 def main():
@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)         # ev.py:198
     ap.add_argument("--chunk", type=int, default=25)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--eager", action="store_true", help="launch every chunk eagerly (no CUDA graph)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -42,14 +43,15 @@ def main():
     model = DeepVAE(**parse_flags(**CIFAR10_16L)).to(dev).eval()
     x = torch.randint(0, 256, (args.batch, 32, 32, 3), generator=torch.Generator().manual_seed(7)).float().to(dev)
     torch.manual_seed(1000 + rank)                            # different importance samples per rank
-    importance_log_likelihood(model, x, 2 * args.chunk * world, args.chunk, world, rank)   # warm-up
+    chunks = None if args.eager else GraphedChunks(model, x)
+    importance_log_likelihood(model, x, 2 * args.chunk * world, args.chunk, world, rank, chunks=chunks)   # warm-up
     if world > 1:
         dist.barrier(device_ids=[local])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.reps):
-        logp = importance_log_likelihood(model, x, args.samples, args.chunk, world, rank)
+        logp = importance_log_likelihood(model, x, args.samples, args.chunk, world, rank, chunks=chunks)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -60,7 +62,7 @@ def main():
         print(json.dumps({"metric": "cifar10_16layer_is_eval_sample_images_per_sec",
                           "value": args.samples * args.batch / sec, "unit": "sample-images/s", "n_gpus": world,
                           "seconds_per_batch": sec, "num_importance_samples": args.samples, "batch": args.batch,
-                          "chunk": args.chunk, "sharding": "by sample", "data": "synthetic",
+                          "chunk": args.chunk, "sharding": "by sample", "cuda_graph": not args.eager, "data": "synthetic",
                           "mean_log_likelihood_nats": float(logp.mean().item())}), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local])
