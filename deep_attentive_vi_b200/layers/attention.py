@@ -110,11 +110,16 @@ class NonlocalResNetBlock(nn.Module):
             self.ln_b_gamma, self.ln_b_beta = nn.Parameter(torch.ones(C)), nn.Parameter(torch.zeros(C))
             self._ln_conv2d = WNConv2d(C, C, **kw)
         self._pad = (-C) % 4
+        # set by util/trainer.py: one leaf view [2d+C, C, 1, 1] over the three adjacent effective kernels
+        self._qkv_w_override = None
 
     def _qkv(self, x):
         d, C, pad = self._key_dim, self._C, self._pad
-        ws = [self.query_conv.kernel(), self.key_conv.kernel(), self.value_conv.kernel()]
         bs = [self.query_conv.bias, self.key_conv.bias, self.value_conv.bias]
+        if self._qkv_w_override is not None:
+            b = torch.cat(bs, 0) if bs[0] is not None else None
+            return to_nhwc(ops.conv2d_bias(to_nchw(x), self._qkv_w_override, b))
+        ws = [self.query_conv.kernel(), self.key_conv.kernel(), self.value_conv.kernel()]
         if pad:   # keep rows 16-byte multiples (C = 138 in the CIFAR-10 pre-processor)
             ws.append(ws[0].new_zeros(pad, C, 1, 1))
             if bs[0] is not None:

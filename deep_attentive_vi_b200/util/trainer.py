@@ -127,7 +127,32 @@ class FlatState:
             woff += pad(o * cols)
         self.W = torch.zeros(woff, device=device)
         self.dW = torch.zeros(woff, device=device)
+        where = {id(m): (off, o, i, h, w) for m, off, o, i, h, w in sizes}
+        # the q | k | v projections of a nonlocal block are ONE 1x1 convolution: when their three
+        # effective kernels are adjacent in W (no alignment gap), the block reads them as one leaf
+        # view [2d+C, C, 1, 1] instead of concatenating three tensors every step
+        from ..layers.attention import NonlocalResNetBlock
+        fused = set()
+        self.qkv_blocks = []
+        for blk in model.modules():
+            if not isinstance(blk, NonlocalResNetBlock) or blk._pad:
+                continue
+            trio = [blk.query_conv, blk.key_conv, blk.value_conv]
+            if not all(id(c) in where for c in trio):
+                continue
+            (oq, nq, C, _, _), (ok_, nk, _, _, _), (ov, nv, _, _, _) = (where[id(c)] for c in trio)
+            if ok_ != oq + nq * C or ov != ok_ + nk * C:
+                continue
+            rows = nq + nk + nv
+            wv = self.W[oq:oq + rows * C].view(rows, 1, 1, C).permute(0, 3, 1, 2)
+            wv.requires_grad_(True)
+            blk._qkv_w_override = wv
+            self.slots.append((wv, "dW", oq, rows * C, True))
+            self.qkv_blocks.append(blk)
+            fused.update(id(c) for c in trio)
         for m, off, o, i, h, w in sizes:
+            if id(m) in fused:
+                continue
             n = o * i * h * w
             wv = self.W[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)       # OHWI memory = channels_last
             wv.requires_grad_(True)
@@ -171,6 +196,8 @@ class FlatState:
         """Detach the model from the fused weight-norm path (it computes its kernels itself again)."""
         for m in getattr(self, "wn_modules", []):
             m._w_override = None
+        for blk in getattr(self, "qkv_blocks", []):
+            blk._qkv_w_override = None
         self.wn_rows = 0
 
 
