@@ -373,6 +373,7 @@ constexpr int kDsStageBytes = 4 * kTileBytes;    // U raw/lo + W raw/lo
 
 struct DsGeom {
     int N, d, C, nkb, nch, ksteps, last_ksteps;  // nch = channel chunks of 32; k-steps of the last one
+    int v2;                                       // N == 256: the 256-column variant (nl_ds256_body)
 };
 
 struct DsArgs {
@@ -613,13 +614,265 @@ __device__ __forceinline__ void nl_ds_body(const CUtensorMap& tmX, const CUtenso
     }
 }
 
+// -----------------------------------------------------------------------------
+// The same gradient for N == 256 (124 of the 128 blocks of the CIFAR-10 model), restructured around the
+// measured cost model "one tcgen05.mma costs ~173 cycles whatever its N": dp = U W^T is computed for ALL
+// 256 columns at once (N = 256 instructions: half as many as two 128-column blocks), into TMEM columns
+// [128,384).  Shared memory is time-multiplexed: while dp accumulates, both 96 KB ring stages hold
+// U (128 rows) and W (256 rows) channel chunks; afterwards the same bytes receive the two images of the
+// two Y blocks, and S / dS / dX proceed block by block as in the general kernel.
+//   TMEM: S | dS_hi [0,128)   dp | dS_lo [128,384)   dX [384,416)
+// -----------------------------------------------------------------------------
+constexpr int kD2OCol = 384;
+constexpr int kD2StageBytes = 6 * kTileBytes;    // U raw/lo (16 KB each) + W raw/lo (32 KB each)
+
+struct D2Bars {
+    uint64_t x_full, x_ready;
+    uint64_t uw_full[2], uw_ready[2], uw_empty[2];
+    uint64_t y_full[2], y_ready[2];
+    uint64_t dp_done, s_full, ds_full, o_full;
+    uint32_t tmem_base;
+};
+
+template <int MODE>
+__device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const CUtensorMap& tmYmn,
+                                              const CUtensorMap& tmU, const CUtensorMap& tmW, const DsArgs& a,
+                                              const DsGeom& g, uint8_t* smem_raw) {
+    __shared__ D2Bars bars;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, r0 = blockIdx.x * kPvM;
+
+    auto sU = [&](int s) { return smem + s * kD2StageBytes; };                       // raw, +16K lo
+    auto sW = [&](int s) { return smem + s * kD2StageBytes + 2 * kTileBytes; };      // raw 32K, +32K lo
+    uint8_t* sXr = smem + 2 * kD2StageBytes;
+    uint8_t* sXl = sXr + kTileBytes;
+    auto sYr = [&](int cb) { return smem + cb * 4 * kTileBytes; };                   // K-major image of Y block cb
+    auto sYl = [&](int cb) { return smem + cb * 4 * kTileBytes + kTileBytes; };
+    auto sMr = [&](int cb) { return smem + cb * 4 * kTileBytes + 2 * kTileBytes; };  // MN-major image
+    auto sMl = [&](int cb) { return smem + cb * 4 * kTileBytes + 3 * kTileBytes; };
+
+    if (tid == 0) {
+        mbar_init(&bars.x_full, 1);
+        mbar_init(&bars.x_ready, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.uw_full[i], 1);
+            mbar_init(&bars.uw_ready[i], 256);
+            mbar_init(&bars.uw_empty[i], 1);
+            mbar_init(&bars.y_full[i], 1);
+            mbar_init(&bars.y_ready[i], 128);
+        }
+        mbar_init(&bars.dp_done, 1);
+        mbar_init(&bars.s_full, 1);
+        mbar_init(&bars.ds_full, 256);
+        mbar_init(&bars.o_full, 1);
+        mbar_init_fence();
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmYmn);
+        tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmW);
+    }
+    if (warp == 10) tmem_alloc(&bars.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars.tmem_base;
+    const int nch = g.nch;
+
+    // dS phase, shared by warps 0-3 (columns 0..63 of each block) and warps 4-7 (columns 64..127): thread
+    // r % 128 <-> row r0 + r % 128 <-> TMEM lane r % 128 (a warp may touch the lanes 32 * (warp % 4) ...)
+    const int srow = tid & 127;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float scale = a.scale ? __ldg(a.scale) : 1.f;
+    auto ds_phase = [&](int half) {
+        const float sc = scale * kLog2e;
+        const int64_t row = (int64_t)b * g.N + r0 + srow;
+        const float* lse_b = a.lse + (int64_t)b * g.N;
+        const float* E_b = a.E + (int64_t)b * g.N;
+        float lse_r = 0.f, E_r = 0.f;
+        if (MODE == 0) { lse_r = __ldg(a.lse + row) * kLog2e; E_r = __ldg(a.E + row); }
+        float dsc = 0.f;
+        for (int cb = 0; cb < 2; ++cb) {
+            mbar_wait(&bars.s_full, cb & 1);          // S(cb) done; the dp MMAs were issued (and finished) before it
+            tc_fence_after();
+            const uint32_t dpc = 128 + cb * 128;
+#pragma unroll 1
+            for (int c32 = 2 * half; c32 < 2 * half + 2; ++c32) {
+                float sv[32], dp[32];
+                tmem_ld32(trow + c32 * 32, sv);
+                tmem_ld32(trow + dpc + c32 * 32, dp);
+                tmem_ld_wait();
+                float hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float lj = lse_r, ej = E_r;
+                    if (MODE == 1) {
+                        const int col = cb * kPvKB + c32 * 32 + j;
+                        lj = __ldg(lse_b + col) * kLog2e;
+                        ej = __ldg(E_b + col);
+                    }
+                    const float p = exp2f(fmaf(sv[j], sc, -lj));
+                    const float ds = p * (dp[j] - ej);
+                    dsc = fmaf(ds, sv[j], dsc);
+                    hi[j] = ds;
+                    lo[j] = lo_tf32(ds);
+                }
+                tmem_st16(trow + c32 * 32, hi);
+                tmem_st16(trow + c32 * 32 + 16, hi + 16);
+                tmem_st16(trow + dpc + c32 * 32, lo);
+                tmem_st16(trow + dpc + c32 * 32 + 16, lo + 16);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.ds_full);
+        }
+        if (MODE == 0 && a.dscale) {
+            dsc = group_sum<32>(dsc);
+            if (lane == 0) atomicAdd(a.dscale, dsc * __ldg(a.gamma));
+        }
+    };
+
+    if (warp < 4) {
+        // ---- warps 0-3: lo passes while dp accumulates, first half of the dS phase, epilogue ----
+        for (int gch = 0; gch < nch; ++gch) {
+            const int s = gch & 1;
+            mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
+            lo_pass(sU(s), sU(s) + kTileBytes, kTileBytes / 16, tid, 256);
+            lo_pass(sW(s), sW(s) + 2 * kTileBytes, 2 * kTileBytes / 16, tid, 256);
+            fence_async_smem();
+            mbar_arrive(&bars.uw_ready[s]);
+        }
+        ds_phase(0);
+        const float gs = __ldg(a.gamma) * scale;
+        mbar_wait(&bars.o_full, 0);
+        tc_fence_after();
+        float o[32];
+        tmem_ld32(trow + kD2OCol, o);
+        tmem_ld_wait();
+        float* orow = a.out + ((int64_t)b * g.N + r0 + srow) * a.out_s;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+            if (4 * q4 < g.d)
+                *reinterpret_cast<float4*>(orow + 4 * q4) =
+                    make_float4(gs * o[4 * q4], gs * o[4 * q4 + 1], gs * o[4 * q4 + 2], gs * o[4 * q4 + 3]);
+        tc_fence_before();
+    } else if (warp < 8) {
+        // ---- lo passes: X, the U / W channel chunks, then the four Y tiles ----
+        const int lt = tid - 128;
+        mbar_wait(&bars.x_full, 0);
+        lo_pass(sXr, sXl, kTileBytes / 16, lt, 128);
+        fence_async_smem();
+        mbar_arrive(&bars.x_ready);
+        for (int gch = 0; gch < nch; ++gch) {
+            const int s = gch & 1;
+            mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
+            lo_pass(sU(s), sU(s) + kTileBytes, kTileBytes / 16, tid, 256);            // threads 128..255 of 256
+            lo_pass(sW(s), sW(s) + 2 * kTileBytes, 2 * kTileBytes / 16, tid, 256);
+            fence_async_smem();
+            mbar_arrive(&bars.uw_ready[s]);
+        }
+        for (int cb = 0; cb < 2; ++cb) {
+            mbar_wait(&bars.y_full[cb], 0);
+            lo_pass(sYr(cb), sYl(cb), kTileBytes / 16, lt, 128);
+            lo_pass(sMr(cb), sMl(cb), kTileBytes / 16, lt, 128);
+            fence_async_smem();
+            mbar_arrive(&bars.y_ready[cb]);
+        }
+        ds_phase(1);
+        tc_fence_before();
+    } else if (warp == 8) {
+        if (lane == 0) {                                   // TMA: X now; the Y tiles once the ring memory is free
+            mbar_expect_tx(&bars.x_full, kTileBytes);
+            tma_load_3d(sXr, &tmX, 0, r0, b, &bars.x_full);
+            mbar_wait(&bars.dp_done, 0);                   // every dp MMA has read its operands: the ring is free
+            for (int cb = 0; cb < 2; ++cb) {
+                mbar_expect_tx(&bars.y_full[cb], 2 * kTileBytes);
+                tma_load_3d(sYr(cb), &tmY, 0, cb * kPvKB, b, &bars.y_full[cb]);
+                tma_load_3d(sMr(cb), &tmYmn, 0, cb * kPvKB, b, &bars.y_full[cb]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        if (lane == 0) {                                   // TMA: U (128 rows) and W (2 x 128 rows) channel chunks
+            for (int gch = 0; gch < nch; ++gch) {
+                const int s = gch & 1;
+                if (gch >= 2) mbar_wait(&bars.uw_empty[s], ((gch >> 1) - 1) & 1);
+                mbar_expect_tx(&bars.uw_full[s], 3 * kTileBytes);
+                tma_load_3d(sU(s), &tmU, gch * 32, r0, b, &bars.uw_full[s]);
+                tma_load_3d(sW(s), &tmW, gch * 32, 0, b, &bars.uw_full[s]);
+                tma_load_3d(sW(s) + kTileBytes, &tmW, gch * 32, kPvKB, b, &bars.uw_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            const uint32_t idesc_s = idesc_tf32(kPvM, kPvKB, false, false);
+            const uint32_t idesc_p = idesc_tf32(kPvM, 256, false, false);
+            const uint32_t idesc_o = idesc_tf32(kPvM, 32, false, true);
+            for (int gch = 0; gch < nch; ++gch) {               // dp[128 x 256] += U_chunk W_chunk^T
+                const int s = gch & 1;
+                mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
+                mbar_wait(&bars.uw_ready[s], (gch >> 1) & 1);
+                tc_fence_after();
+                const uint32_t aUr = smem_u32(sU(s)), aUl = aUr + kTileBytes;
+                const uint32_t aWr = smem_u32(sW(s)), aWl = aWr + 2 * kTileBytes;
+                const int nks = gch == nch - 1 ? g.last_ksteps : 4;
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint32_t o = ks * 32;
+                    mma_tf32(tmem + 128, desc_kmajor(aUl + o), desc_kmajor(aWr + o), idesc_p, (gch | ks) != 0);
+                    mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWl + o), idesc_p, true);
+                    mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWr + o), idesc_p, true);
+                }
+                tc_commit(&bars.uw_empty[s]);
+            }
+            tc_commit(&bars.dp_done);
+            mbar_wait(&bars.x_full, 0);
+            mbar_wait(&bars.x_ready, 0);
+            const uint32_t aXr = smem_u32(sXr), aXl = smem_u32(sXl);
+            for (int cb = 0; cb < 2; ++cb) {
+                mbar_wait(&bars.y_full[cb], 0);
+                mbar_wait(&bars.y_ready[cb], 0);
+                tc_fence_after();
+                const uint32_t aYr = smem_u32(sYr(cb)), aYl = smem_u32(sYl(cb));
+                const uint32_t aMr = smem_u32(sMr(cb)), aMl = smem_u32(sMl(cb));
+                for (int ks = 0; ks < g.ksteps; ++ks) {
+                    const uint32_t o = ks * 32;
+                    mma_tf32(tmem, desc_kmajor(aXl + o), desc_kmajor(aYr + o), idesc_s, ks > 0);
+                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYl + o), idesc_s, true);
+                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYr + o), idesc_s, true);
+                }
+                tc_commit(&bars.s_full);
+                mbar_wait(&bars.ds_full, cb & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < kPvKB / 8; ++ks) {
+                    const uint32_t dh = tmem + ks * 8, dl = tmem + 128 + cb * 128 + ks * 8;
+                    const uint32_t o = ks * 1024;
+                    mma_tf32_ts(tmem + kD2OCol, dl, desc_mnmajor(aMr + o, kTileBytes), idesc_o, (cb | ks) != 0);
+                    mma_tf32_ts(tmem + kD2OCol, dh, desc_mnmajor(aMl + o, kTileBytes), idesc_o, true);
+                    mma_tf32_ts(tmem + kD2OCol, dh, desc_mnmajor(aMr + o, kTileBytes), idesc_o, true);
+                }
+            }
+            tc_commit(&bars.o_full);
+            tc_fence_before();
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    if (warp == 10) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kDsThreads, 1)
 nl_ds_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
              const __grid_constant__ CUtensorMap tmYmn, const __grid_constant__ CUtensorMap tmU,
              const __grid_constant__ CUtensorMap tmW, const DsArgs a, const DsGeom g) {
     extern __shared__ uint8_t smem_raw[];
-    nl_ds_body<MODE>(tmX, tmY, tmYmn, tmU, tmW, a, g, smem_raw);
+    if (g.v2) nl_ds256_body<MODE>(tmX, tmY, tmYmn, tmU, tmW, a, g, smem_raw);
+    else nl_ds_body<MODE>(tmX, tmY, tmYmn, tmU, tmW, a, g, smem_raw);
 }
 
 // The three gradient kernels of one block in ONE launch (role = blockIdx.z): each of them alone fills
@@ -638,8 +891,13 @@ __global__ void __launch_bounds__(kDsThreads, 1)
 nl_bwd_fused_kernel(const __grid_constant__ BwdFusedParams p) {
     extern __shared__ uint8_t smem_raw[];
     if (blockIdx.z == 0) nl_pv_body<1>(p.pvX, p.pvY, p.pvW, p.pva, p.pvg, smem_raw);
-    else if (blockIdx.z == 1) nl_ds_body<0>(p.dsX[0], p.dsY[0], p.dsYmn[0], p.dsU[0], p.dsW[0], p.dsa[0], p.dsg, smem_raw);
-    else nl_ds_body<1>(p.dsX[1], p.dsY[1], p.dsYmn[1], p.dsU[1], p.dsW[1], p.dsa[1], p.dsg, smem_raw);
+    else if (blockIdx.z == 1) {
+        if (p.dsg.v2) nl_ds256_body<0>(p.dsX[0], p.dsY[0], p.dsYmn[0], p.dsU[0], p.dsW[0], p.dsa[0], p.dsg, smem_raw);
+        else nl_ds_body<0>(p.dsX[0], p.dsY[0], p.dsYmn[0], p.dsU[0], p.dsW[0], p.dsa[0], p.dsg, smem_raw);
+    } else {
+        if (p.dsg.v2) nl_ds256_body<1>(p.dsX[1], p.dsY[1], p.dsYmn[1], p.dsU[1], p.dsW[1], p.dsa[1], p.dsg, smem_raw);
+        else nl_ds_body<1>(p.dsX[1], p.dsY[1], p.dsYmn[1], p.dsU[1], p.dsW[1], p.dsa[1], p.dsg, smem_raw);
+    }
 }
 
 // E[b,i] = <dy[b,i,:], O[b,i,:]> (one warp per row); dgamma += sum E
@@ -772,15 +1030,22 @@ int nonlocal_dv_tc_launch(const float* Q, const float* K, const float* lse, cons
 }
 
 
-template <int MODE>
-static int ds_launch(const char* fn, const float* X, const float* Y, const float* U, const float* W, int64_t x_s,
-                     int64_t y_s, int64_t u_s, int64_t w_s, const DsArgs& a, int B, int N, int d, int C,
-                     cudaStream_t st) {
+static DsGeom ds_geom(int N, int d, int C) {
     DsGeom g;
     g.N = N; g.d = d; g.C = C; g.nkb = N / kPvKB;
     g.nch = (C + 31) / 32;
     g.ksteps = (d + 7) / 8;
     g.last_ksteps = (C - 32 * (g.nch - 1) + 7) / 8;
+    static const bool no_v2 = [] { const char* e = getenv("DAVI_NL_DS"); return e && strcmp(e, "v1") == 0; }();
+    g.v2 = (N == 256 && !no_v2) ? 1 : 0;
+    return g;
+}
+
+template <int MODE>
+static int ds_launch(const char* fn, const float* X, const float* Y, const float* U, const float* W, int64_t x_s,
+                     int64_t y_s, int64_t u_s, int64_t w_s, const DsArgs& a, int B, int N, int d, int C,
+                     cudaStream_t st) {
+    const DsGeom g = ds_geom(N, d, C);
     CUtensorMap tmX, tmY, tmYmn, tmU, tmW;
     int rc;
     if ((rc = make_tmap_rows(&tmX, X, d, N, B, x_s, kPvM, false))) return rc;
@@ -792,15 +1057,6 @@ static int ds_launch(const char* fn, const float* X, const float* Y, const float
     DAVI_CUDA(cudaFuncSetAttribute(nl_ds_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nl_ds_kernel<MODE><<<dim3(N / kPvM, B), kDsThreads, smem, st>>>(tmX, tmY, tmYmn, tmU, tmW, a, g);
     return check_launch(fn);
-}
-
-static DsGeom ds_geom(int N, int d, int C) {
-    DsGeom g;
-    g.N = N; g.d = d; g.C = C; g.nkb = N / kPvKB;
-    g.nch = (C + 31) / 32;
-    g.ksteps = (d + 7) / 8;
-    g.last_ksteps = (C - 32 * (g.nch - 1) + 7) / 8;
-    return g;
 }
 
 // Full gradient on the tensor cores.  E: workspace [B,N]; dgs = {dgamma, dscale} (overwritten).

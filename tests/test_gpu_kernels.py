@@ -125,10 +125,23 @@ def test_nonlocal_matches_oracle(cuda, N_hw, d, C):
     # N % 128 == 0 runs on the tensor cores with 3xTF32 error compensation (fp32-grade products):
     # stated tolerance 1e-5 on the output, 3e-5 on every gradient, relative to the tensor's max-abs
     assert rel_err(y, want) < 1e-5
-    for got, w, name in zip(ins, rins, "q k v x scale gamma".split()):
+    for got, w, name in zip(ins[:4], rins[:4], "q k v x".split()):
         e = rel_err(got.grad, w.grad)
-        # the two scalar gradients are sums of ~1e6 signed terms reduced with atomics: 1e-4
-        assert e < (1e-4 if name in ("scale", "gamma") else 3e-5), (name, e)
+        assert e < 3e-5, (name, e)
+    # The two scalar gradients are sums of B * N * N (scale) / B * N * C (gamma) signed terms that cancel
+    # almost completely (every row of dS sums to zero; for the (16, 8, 72) case the sum is 3e-5 of the sum of
+    # magnitudes), so their error is stated against the sum of the term magnitudes: 1e-6 (fp32-grade terms).
+    N = N_hw * N_hw
+    q2, k2, v2, go2 = [t.double().reshape(B, N, -1) for t in (q, k, v, go)]
+    S = q2 @ k2.transpose(1, 2)
+    P = torch.softmax(float(scale) * S, -1)
+    dP = (float(gamma) * go2) @ v2.transpose(1, 2)
+    dS = P * (dP - (P * dP).sum(-1, keepdim=True))
+    mag_scale = (dS * S).abs().sum().item()
+    mag_gamma = (go2 * (P @ v2)).abs().sum().item()
+    assert abs((dS * S).sum().item() - rins[4].grad.item()) < 1e-9 * mag_scale     # the decomposition is the gradient
+    assert abs(ins[4].grad.item() - rins[4].grad.item()) < 1e-6 * mag_scale, "scale"
+    assert abs(ins[5].grad.item() - rins[5].grad.item()) < 1e-6 * mag_gamma, "gamma"
 
 
 def test_nonlocal_exact_path_is_fp32_accurate(cuda, monkeypatch):
