@@ -12,8 +12,8 @@
 // One CTA owns 128 rows (queries in the forward, keys for dV) of one image:
 //   warps 0-3   softmax: thread r <-> row r <-> TMEM lane r; P chunks go back into TMEM
 //               (tcgen05.st) and feed the P*V MMAs as TMEM-resident A operands
-//   warps 4-5   lo pass of the row tile X and the column blocks Y (K-major, SWIZZLE_128B)
-//   warps 6-7   lo pass of the value chunks W (MN-major, SWIZZLE_128B_BASE32B)
+//   warps 4-7   lo passes, in the order the MMAs consume them: the row tile X and the column blocks Y
+//               (K-major, SWIZZLE_128B), the value chunks W (MN-major, SWIZZLE_128B_BASE32B)
 //   warp  8     TMA producer of X / Y       warp 9   TMA producer of W
 //   warp 10     one thread issues every tcgen05.mma / tcgen05.commit
 // The [B,N,N] matrix exists only as 128x128 fp32 blocks in TMEM.  Forward = two
@@ -71,10 +71,20 @@ struct PvBars {
 };
 
 // elementwise lo pass over a tile that TMA wrote (same swizzled offsets in both buffers)
-__device__ __forceinline__ void lo_pass(const uint8_t* raw, uint8_t* lo, int n_float4, int lt, int nthreads) {
-    const float4* src = reinterpret_cast<const float4*>(raw);
-    float4* dst = reinterpret_cast<float4*>(lo);
-    for (int i = lt; i < n_float4; i += nthreads) dst[i] = lo4_tf32(src[i]);
+// (four independent loads in flight per thread: the two buffers never overlap)
+__device__ __forceinline__ void lo_pass(const uint8_t* __restrict__ raw, uint8_t* __restrict__ lo, int n_float4,
+                                        int lt, int nthreads) {
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(raw);
+    float4* __restrict__ dst = reinterpret_cast<float4*>(lo);
+    int i = lt;
+    for (; i + 3 * nthreads < n_float4; i += 4 * nthreads) {
+        const float4 v0 = src[i], v1 = src[i + nthreads], v2 = src[i + 2 * nthreads], v3 = src[i + 3 * nthreads];
+        dst[i] = lo4_tf32(v0);
+        dst[i + nthreads] = lo4_tf32(v1);
+        dst[i + 2 * nthreads] = lo4_tf32(v2);
+        dst[i + 3 * nthreads] = lo4_tf32(v3);
+    }
+    for (; i < n_float4; i += nthreads) dst[i] = lo4_tf32(src[i]);
 }
 
 template <int MODE>
@@ -100,10 +110,10 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
 
     if (tid == 0) {
         mbar_init(&bars.x_full, 1);
-        mbar_init(&bars.x_ready, 64);
+        mbar_init(&bars.x_ready, 128);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.y_full[i], 1);
-            mbar_init(&bars.y_ready[i], 64);
+            mbar_init(&bars.y_ready[i], 128);
             mbar_init(&bars.y_empty[i], 1);
             mbar_init(&bars.p_full[i], 128);
             mbar_init(&bars.p_empty[i], 1);
@@ -113,7 +123,7 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
         mbar_init(&bars.o_full, 1);
         for (int s = 0; s < kPvMaxStages; ++s) {
             mbar_init(&bars.w_full[s], 1);
-            mbar_init(&bars.w_ready[s], 64);
+            mbar_init(&bars.w_ready[s], 128);
             mbar_init(&bars.w_empty[s], 1);
         }
         mbar_init_fence();
@@ -124,6 +134,14 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
     if (warp == 10) tmem_alloc(&bars.tmem_base, 512);
     if (MODE == 1)
         for (int i = tid; i < g.N; i += blockDim.x) sStats[i] = a.lse_in[(int64_t)b * g.N + i] * kLog2e;
+    if (MODE == 0) {                                       // the residual input is read in the epilogue: pull it into L2 now
+        const int lines = (g.C * 4 + 127) / 128;
+        for (int i = tid; i < kPvM * lines; i += blockDim.x) {
+            const int rr = i / lines, ln = i - rr * lines;
+            const float* p = a.x + ((int64_t)b * g.N + r0 + rr) * a.x_s + ln * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -199,33 +217,38 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                     make_float4(o[4 * q4] * rs, o[4 * q4 + 1] * rs, o[4 * q4 + 2] * rs, o[4 * q4 + 3] * rs);
         }
         tc_fence_before();
-    } else if (warp < 6) {
+    } else if (warp < 8) {
         // =====================================================================
-        // lo pass of X and of the Y blocks
+        // lo passes (128 threads), in the order the MMA thread consumes the operands:
+        // X, the pass-A Y blocks, the first pass-B Y block, then per block the next Y and its eight W chunks
         // =====================================================================
         const int lt = tid - 128;
         mbar_wait(&bars.x_full, 0);
-        lo_pass(sXr, sXl, kTileBytes / 16, lt, 64);
+        lo_pass(sXr, sXl, kTileBytes / 16, lt, 128);
         fence_async_smem();
         mbar_arrive(&bars.x_ready);
-        for (int u = 0; u < nuse; ++u) {
+        int u = 0;
+        auto y_lo = [&]() {
             const int buf = u & 1;
             mbar_wait(&bars.y_full[buf], (u >> 1) & 1);
-            lo_pass(sYr(buf), sYl(buf), kTileBytes / 16, lt, 64);
+            lo_pass(sYr(buf), sYl(buf), kTileBytes / 16, lt, 128);
             fence_async_smem();
             mbar_arrive(&bars.y_ready[buf]);
-        }
-    } else if (warp < 8) {
-        // =====================================================================
-        // lo pass of the W chunks
-        // =====================================================================
-        const int lt = tid - 192;
-        for (int gc = 0; gc < nchunks; ++gc) {
-            const int s = gc % g.stages;
-            mbar_wait(&bars.w_full[s], (gc / g.stages) & 1);
-            lo_pass(sWr(s), sWl(s), w_bytes / 16, lt, 64);
-            fence_async_smem();
-            mbar_arrive(&bars.w_ready[s]);
+            ++u;
+        };
+        if (MODE == 0)
+            for (int kb = 0; kb < g.nkb; ++kb) y_lo();
+        y_lo();
+        int gc = 0;
+        for (int kb = 0; kb < g.nkb; ++kb) {
+            if (kb + 1 < g.nkb) y_lo();
+            for (int c = 0; c < kPvChunks; ++c, ++gc) {
+                const int s = gc % g.stages;
+                mbar_wait(&bars.w_full[s], (gc / g.stages) & 1);
+                lo_pass(sWr(s), sWl(s), w_bytes / 16, lt, 128);
+                fence_async_smem();
+                mbar_arrive(&bars.w_ready[s]);
+            }
         }
     } else if (warp == 8) {
         if (lane == 0) {                                   // TMA producer: X tile, then the Y blocks
@@ -325,24 +348,42 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
-    // ---- epilogue, part 2: every thread streams the staged tile out with coalesced accesses ----
+    // ---- epilogue, part 2: every thread streams the staged tile out with coalesced accesses; the loads of
+    //      x go out eight at a time so that one DRAM round trip serves eight stores ----
     {
         const float gamma = __ldg(a.gamma);
         const int C4 = g.C >> 2, ld = g.Cp + 4;
         const float* tile = reinterpret_cast<const float*>(smem);
         const int64_t row0 = (int64_t)b * g.N + r0;
-        for (int idx = tid; idx < kPvM * C4; idx += blockDim.x) {
-            const int rr = idx / C4, c = (idx - rr * C4) * 4;
-            const float4 o = *reinterpret_cast<const float4*>(tile + (size_t)rr * ld + c);
+        const int total = kPvM * C4, nthr = blockDim.x;
+        constexpr int U = 8;
+        for (int base = tid; base < total; base += U * nthr) {
+            float4 xi[U];
             if (MODE == 0) {
-                const float4 xi = ld_stream4(a.x + (row0 + rr) * a.x_s + c);
-                st_stream4(a.y + (row0 + rr) * a.y_s + c,
-                           make_float4(fmaf(gamma, o.x, xi.x), fmaf(gamma, o.y, xi.y), fmaf(gamma, o.z, xi.z),
-                                       fmaf(gamma, o.w, xi.w)));
-                if (a.o_save) st_stream4(a.o_save + (row0 + rr) * a.o_s + c, o);
-            } else {
-                st_stream4(a.out + (row0 + rr) * a.out_s + c,
-                           make_float4(gamma * o.x, gamma * o.y, gamma * o.z, gamma * o.w));
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = base + u * nthr;
+                    if (idx < total) {
+                        const int rr = idx / C4, c = (idx - rr * C4) * 4;
+                        xi[u] = ld_stream4(a.x + (row0 + rr) * a.x_s + c);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * nthr;
+                if (idx >= total) break;
+                const int rr = idx / C4, c = (idx - rr * C4) * 4;
+                const float4 o = *reinterpret_cast<const float4*>(tile + (size_t)rr * ld + c);
+                if (MODE == 0) {
+                    st_stream4(a.y + (row0 + rr) * a.y_s + c,
+                               make_float4(fmaf(gamma, o.x, xi[u].x), fmaf(gamma, o.y, xi[u].y),
+                                           fmaf(gamma, o.z, xi[u].z), fmaf(gamma, o.w, xi[u].w)));
+                    if (a.o_save) st_stream4(a.o_save + (row0 + rr) * a.o_s + c, o);
+                } else {
+                    st_stream4(a.out + (row0 + rr) * a.out_s + c,
+                               make_float4(gamma * o.x, gamma * o.y, gamma * o.z, gamma * o.w));
+                }
             }
         }
     }
@@ -911,7 +952,16 @@ nl_rowdot_kernel(const float* __restrict__ dy, const float* __restrict__ O, floa
     if (row < rows) {
         const float* a = dy + row * dy_s;
         const float* o = O + row * o_s;
-        for (int c = lane; c < C4; c += 32) e += dot4(ld_stream4(a + 4 * c), ld_stream4(o + 4 * c));
+        float4 av[3], ov[3];                       // C <= 384: all six loads of a lane in flight at once
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int c = lane + 32 * u;
+            if (c < C4) { av[u] = ld_stream4(a + 4 * c); ov[u] = ld_stream4(o + 4 * c); }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (lane + 32 * u < C4) e += dot4(av[u], ov[u]);
+        for (int c = lane + 96; c < C4; c += 32) e += dot4(ld_stream4(a + 4 * c), ld_stream4(o + 4 * c));
         e = group_sum<32>(e);
         if (lane == 0) E[row] = e;
     }
