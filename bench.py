@@ -213,6 +213,14 @@ def dw_roofline(batch, device):
 # this repo's arm
 # ---------------------------------------------------------------------------
 
+CONV_NOTE = {
+    "3xtf32": "cuDNN on TF32 tensor cores with 3xTF32 error compensation (fp32-grade: operands split hi/lo by "
+              "davi_split_tf32, three products accumulated in fp32 over a tripled contraction axis)",
+    "fp32": "cuDNN fp32 (CUDA cores)",
+    "tf32": "cuDNN plain TF32 (opt-in; operands truncated to 10 mantissa bits, below the reference's fp32)",
+}
+
+
 def run_davi(args):
     import torch
     import torch.distributed as dist
@@ -231,18 +239,10 @@ def run_davi(args):
     if not os.path.exists(_lib.LIB_PATH):
         build.build()
     _lib.load()
-    # hot-path kernels compute in fp32; the host-side cuDNN convolutions use TF32 tensor cores
-    torch.backends.cudnn.allow_tf32 = not args.fp32_convs
-    torch.backends.cuda.matmul.allow_tf32 = not args.fp32_convs
+    from deep_attentive_vi_b200 import ops
     torch.backends.cudnn.benchmark = True
 
     B = args.batch
-    torch.manual_seed(0)
-    model = DeepVAE(**parse_flags(**CIFAR10_16L)).to(device)
-    trainer = Trainer(model, device=device, world_size=world, rank=rank, use_graph=not args.eager,
-                      graph_warmup=min(3, max(1, args.warmup - 1)))
-    nparams = model.count_params()
-
     g = torch.Generator().manual_seed(1000 + rank)
     nbuf = 4
     host = [torch.randint(0, 256, (B, 32, 32, 3), generator=g).float().pin_memory() for _ in range(nbuf)]
@@ -266,28 +266,47 @@ def run_davi(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def resident_step(s):
-        trainer.train_step(dev_in[s % nbuf])
+    def measure(convs, sampler=None):
+        """Whole train steps of the model with the host-side convolutions in precision `convs`
+        (the hot-path kernels always compute in fp32): device-resident and end-to-end timings."""
+        ops.set_conv_precision(convs)
+        torch.manual_seed(0)
+        model = DeepVAE(**parse_flags(**CIFAR10_16L)).to(device)
+        trainer = Trainer(model, device=device, world_size=world, rank=rank, use_graph=not args.eager,
+                          graph_warmup=min(3, max(1, args.warmup - 1)))
+        last = {}
 
-    last = {}
+        def resident_step(s):
+            trainer.train_step(dev_in[s % nbuf])
 
-    def e2e_step(s):
-        x = host[s % nbuf].to(device, non_blocking=True)          # H2D from pinned memory
-        nll, kl = trainer.train_step(x)
-        last["loss"] = float((nll.mean() + kl.mean()).item())      # D2H read of the step's loss
+        def e2e_step(s):
+            x = host[s % nbuf].to(device, non_blocking=True)          # H2D from pinned memory
+            nll, kl = trainer.train_step(x)
+            last["loss"] = float((nll.mean() + kl.mean()).item())      # D2H read of the step's loss
 
-    for s in range(args.warmup):
-        resident_step(s)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    calls0 = _lib.launch_count()
-    ms = timed(resident_step, args.steps)
-    launches = _lib.launch_count() - calls0
-    for s in range(min(args.warmup, 2)):
-        e2e_step(s)
-    ms_e2e = timed(e2e_step, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+        for s in range(args.warmup):
+            resident_step(s)
+        if sampler is not None:
+            sampler.start()
+        calls0 = _lib.launch_count()
+        ms = timed(resident_step, args.steps)
+        launches = _lib.launch_count() - calls0
+        for s in range(min(args.warmup, 2)):
+            e2e_step(s)
+        ms_e2e = timed(e2e_step, args.steps)
+        clocks = sampler.stop() if sampler is not None else None
+        out = {"ms": ms, "ms_e2e": ms_e2e, "launches": launches, "loss": last.get("loss"), "clocks": clocks,
+               "params": model.count_params()}
+        del trainer, model
+        torch.cuda.empty_cache()
+        return out
+
+    r = measure(args.convs, ClockSampler(local) if rank == 0 else None)
+    ms, ms_e2e, launches, clocks, nparams = r["ms"], r["ms_e2e"], r["launches"], r["clocks"], r["params"]
+    last = {"loss": r["loss"]}
+    alt = None
+    if args.alt_convs and args.alt_convs != args.convs:
+        alt = measure(args.alt_convs)
 
     value = B * world * args.steps / (ms / 1e3)
     e2e_val = B * world * args.steps / (ms_e2e / 1e3)
@@ -296,7 +315,7 @@ def run_davi(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "params": nparams,
-                   "parallelism": f"dp{world}", "cuda_graph": not args.eager, "convs": "cuDNN fp32" if args.fp32_convs else "cuDNN tf32",
+                   "parallelism": f"dp{world}", "cuda_graph": not args.eager, "convs": CONV_NOTE[args.convs],
                    "l2": "inputs (2 GB activations per step) exceed L2; dw-attention roofline launches rotate over "
                          "operand sets with a total footprint > 3x L2 (every launch reads cold inputs)"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 32 * 32 * 3 * 4,
@@ -304,6 +323,11 @@ def run_davi(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if alt is not None:
+        # opt-in precision, measured in the same run for the record: NOT the headline
+        line["alt_convs"] = {"convs": CONV_NOTE[args.alt_convs], "value": B * world * args.steps / (alt["ms"] / 1e3),
+                             "unit": UNIT, "ms_per_step": alt["ms"] / args.steps,
+                             "e2e_value": B * world * args.steps / (alt["ms_e2e"] / 1e3)}
     if rank == 0:
         if not args.no_roofline:
             peak, which = measured_peak()
@@ -358,12 +382,18 @@ def main():
     ap.add_argument("--impl", default="davi", choices=["davi", "reference"])
     ap.add_argument("--batch", type=int, default=40, help="images per GPU (BASELINE config: 40)")
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
-    ap.add_argument("--fp32-convs", action="store_true", help="disable TF32 in the host-side cuDNN convs")
+    ap.add_argument("--convs", default="3xtf32", choices=["3xtf32", "fp32", "tf32"],
+                    help="precision of the host-side cuDNN convolutions (default: fp32-grade 3xTF32)")
+    ap.add_argument("--alt-convs", default="tf32", choices=["", "3xtf32", "fp32", "tf32"],
+                    help="second precision measured for the record into 'alt_convs' ('' to skip)")
+    ap.add_argument("--fp32-convs", action="store_true", help="same as --convs fp32")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-detail", default="", help="write the per-call dw-attention timings here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.fp32_convs:
+        args.convs = "fp32"
     if args.impl == "reference":
         return run_reference(args)
     return run_davi(args)

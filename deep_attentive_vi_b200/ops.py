@@ -626,8 +626,93 @@ class _ConvBias(torch.autograd.Function):
         return gx, gw, gb, None, None
 
 
+# Precision of the host-side cuDNN convolutions (row f1).  The reference's Conv2D layers are fp32:
+#   "3xtf32" (default)  fp32-grade on the TF32 tensor cores: operands split by davi_split_tf32, the three
+#                       compensated products accumulated by ONE cuDNN convolution over a tripled axis
+#   "fp32"              cuDNN's CUDA-core fp32 kernels (the bit-level yardstick of the parity tests)
+#   "tf32"              plain TF32 (13 operand mantissa bits dropped; opt-in, NOT reference precision)
+CONV_PRECISIONS = ("3xtf32", "fp32", "tf32")
+_conv_precision = "3xtf32"
+
+
+def set_conv_precision(mode):
+    global _conv_precision
+    if mode not in CONV_PRECISIONS:
+        raise ValueError(f"conv precision {mode!r}: expected one of {CONV_PRECISIONS}")
+    _conv_precision = mode
+    torch.backends.cudnn.allow_tf32 = mode != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+
+
+def get_conv_precision():
+    return _conv_precision
+
+
+def split_tf32(t, layout, pattern):
+    """t: NCHW-shaped channels_last tensor (or any contiguous [..., C]) -> its three-part TF32 split.
+    layout 0: channel axis tripled (same memory format); layout 1: batch axis tripled."""
+    _require_cuda(t)
+    if t.dim() == 4:
+        nhwc = t.permute(0, 2, 3, 1)
+        if not nhwc.is_contiguous():
+            nhwc = nhwc.contiguous()
+        B, H, W, C = nhwc.shape
+        out = torch.empty((B, H, W, 3 * C) if layout == 0 else (3 * B, H, W, C), device=t.device, dtype=torch.float32)
+        _lib_call("davi_split_tf32", _p(nhwc), _p(out), B * H * W, C, layout, pattern, _stream())
+        return out.permute(0, 3, 1, 2)
+    t = t.contiguous()
+    C = t.shape[-1]
+    rows = t.numel() // C
+    out = torch.empty((rows, 3 * C) if layout == 0 else (3, rows, C), device=t.device, dtype=torch.float32)
+    _lib_call("davi_split_tf32", _p(t), _p(out), rows, C, layout, pattern, _stream())
+    return out
+
+
+class _ConvBias3x(torch.autograd.Function):
+    """fp32-grade convolution on the TF32 tensor cores.  With a = hi_a + lo_a (davi_split_tf32):
+        y  = conv([x_hi | x_lo | x_hi], [w_hi | w_hi | w_lo])            contraction over 3 * C_in
+        gx = conv_input([gy_hi | gy_lo | gy_hi], [w_hi ; w_hi ; w_lo])   contraction over 3 * C_out
+        gw = conv_weight([x_hi ; x_lo ; x_hi], [gy_hi ; gy_hi ; gy_lo])  contraction over 3 * batch
+    each ONE cuDNN TF32 call with fp32 accumulation (hi parts are exact in TF32, lo parts carry the
+    next 11+ bits)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, padding)
+        return torch.nn.functional.conv2d(split_tf32(x, 0, 0), split_tf32(w, 0, 1), b, stride=stride, padding=padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding = ctx.cfg
+        s = (stride, stride) if isinstance(stride, int) else tuple(stride)
+        p = (padding, padding) if isinstance(padding, int) else tuple(padding)
+        gx = gw = gb = None
+        # aten.convolution_backward takes shape and memory format of the result from its `input` / `weight`
+        # argument: passing x and w themselves keeps both gradients channels_last (no layout copies)
+        if ctx.needs_input_grad[0]:
+            w3 = split_tf32(w, 1, 1)
+            gx = torch.ops.aten.convolution_backward(split_tf32(gy, 0, 0), x, w3, [w3.shape[0]], s, p, (1, 1), False,
+                                                     (0, 0), 1, (True, False, False))[0]
+        if ctx.needs_input_grad[1]:
+            gw = torch.ops.aten.convolution_backward(split_tf32(gy, 1, 1), split_tf32(x, 1, 0), w, [w.shape[0]], s, p,
+                                                     (1, 1), False, (0, 0), 1, (False, True, False))[1]
+        if ctx.needs_input_grad[2]:
+            gb = colsum_nhwc(gy)
+        return gx, gw, gb, None, None
+
+
 def conv2d_bias(x, w, b, stride=1, padding=0):
-    """F.conv2d(x, w, b) on NCHW views of channels_last tensors, with the fast bias gradient."""
-    if b is None or not x.is_cuda:
+    """F.conv2d(x, w, b) on NCHW views of channels_last tensors, with the fast bias gradient, in the
+    precision selected by set_conv_precision()."""
+    if not x.is_cuda:
+        return torch.nn.functional.conv2d(x, w, b, stride=stride, padding=padding)
+    if _conv_precision == "3xtf32":
+        if not torch.backends.cudnn.allow_tf32:
+            raise RuntimeError("conv precision '3xtf32' needs torch.backends.cudnn.allow_tf32 = True "
+                               "(use ops.set_conv_precision)")
+        return _ConvBias3x.apply(x, w, b, stride, padding)
+    if b is None:
         return torch.nn.functional.conv2d(x, w, b, stride=stride, padding=padding)
     return _ConvBias.apply(x, w, b, stride, padding)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DAVI_VERSION 103          /* major*100 + minor */
+#define DAVI_VERSION 104          /* major*100 + minor */
 #define DAVI_MAX_SLOTS 32         /* max stacked layers n of the depth-wise attention */
 
 #define DAVI_OK 0
@@ -314,6 +314,17 @@ int davi_colsum(const float* x, float* out, int64_t rows, int C, int64_t x_s,
  * aggregation under MirroredStrategy, util/trainer.py:160-187). */
 int davi_multi_copy(const float* const* srcs, const int64_t* dst_offsets, const int64_t* sizes,
                     int count, float* dst, davi_stream_t stream);
+
+/* 8(f1)  Operand split for fp32-grade convolutions on the TF32 tensor cores ("3xTF32").
+ * src [rows, C] contiguous -> the three-part operand hi = rna_tf32(v), lo = rna_tf32(v - hi):
+ *   layout 0: dst [rows, 3C]   (parts concatenated along the channel axis)
+ *   layout 1: dst [3, rows, C] (three planes: concatenation along the batch axis)
+ *   pattern 0: parts (hi, lo, hi);  pattern 1: parts (hi, hi, lo)
+ * A TF32 convolution of a pattern-0 operand with a pattern-1 operand over the tripled axis
+ * accumulates hi*hi' + lo*hi' + hi*lo' in fp32: the reference's fp32 Conv2D
+ * (layers/resnet.py:589-601) to ~2^-21 per product. */
+int davi_split_tf32(const float* src, float* dst, int64_t rows, int C, int layout, int pattern,
+                    davi_stream_t stream);
 
 #ifdef __cplusplus
 }

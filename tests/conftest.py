@@ -28,3 +28,21 @@ def cuda():
     from deep_attentive_vi_b200 import build
     build.build()
     return torch.device("cuda:0")
+
+
+@pytest.fixture(params=["3xtf32", "fp32"])
+def convs(request):
+    """Precision of the host-side cuDNN convolutions: the product default (fp32-grade 3xTF32 on the
+    tensor cores) and cuDNN's CUDA-core fp32.  Parity tests run in both, to the same tolerance."""
+    from deep_attentive_vi_b200 import ops
+    ops.set_conv_precision(request.param)
+    yield request.param
+    ops.set_conv_precision("3xtf32")
+
+
+@pytest.fixture
+def fp32_convs():
+    from deep_attentive_vi_b200 import ops
+    ops.set_conv_precision("fp32")
+    yield
+    ops.set_conv_precision("3xtf32")

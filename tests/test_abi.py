@@ -44,7 +44,7 @@ def test_ctypes_table_matches_header(libdavi):
 
 
 def test_version_and_error_text(libdavi):
-    assert libdavi.davi_version() == 103
+    assert libdavi.davi_version() == 104
     rc = libdavi.davi_dw_attn_fwd(None, None, None, None, None, 1, 1, 1, 4, 4,
                                   4, 4, 4, 4, 4, 4, 4, 4, None, None)
     assert rc == -1  # DAVI_EINVAL, nothing launched

@@ -274,10 +274,57 @@ def test_colsum_matches_fp64(cuda, rows, C):
     assert ((got.double() - want).abs().max() / want.abs().max()).item() < 1e-5
 
 
-def test_conv_bias_gradient_path_matches_autograd(cuda):
+def test_split_tf32_parts_are_exact(cuda):
+    """davi_split_tf32: neither part has bits below the TF32 mantissa, hi + lo recovers v to 2^-21, both
+    layouts and both part orders, vector (C % 4 == 0) and scalar paths."""
+    from deep_attentive_vi_b200 import ops
+    torch.manual_seed(1)
+    for rows, C in [(37, 24), (50, 3), (8, 276)]:
+        v = torch.randn(rows, C, device=cuda) * torch.logspace(-6, 6, rows, device=cuda)[:, None]
+        for layout in (0, 1):
+            for pattern in (0, 1):
+                out = ops.split_tf32(v, layout, pattern)
+                parts = out.reshape(rows, 3, C).unbind(1) if layout == 0 else out.unbind(0)
+                hi, lo = (parts[0], parts[1]) if pattern == 0 else (parts[0], parts[2])
+                assert torch.equal(parts[2] if pattern == 0 else parts[1], hi)
+                assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+                assert int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+                assert ((hi.double() + lo.double() - v.double()).abs() <= v.abs().double() * 2.0 ** -21).all()
+                assert ((lo.abs() <= hi.abs() * 2.0 ** -10) | (hi == 0)).all()
+
+
+@pytest.mark.parametrize("B,HW,ci,co,k,stride,pad", [(4, 16, 24, 32, 3, 1, 1), (3, 32, 3, 32, 3, 1, 1),
+                                                      (2, 16, 276, 584, 1, 1, 0), (4, 16, 40, 48, 3, 2, (1, 1)),
+                                                      (40, 16, 128, 128, 3, 1, 1)])
+def test_conv_3xtf32_is_fp32_grade(cuda, B, HW, ci, co, k, stride, pad):
+    """The default conv precision (split operands, one TF32 cuDNN call over a tripled contraction axis)
+    against an fp64 convolution: output and all three gradients within 2e-5 of the tensor's max-abs.
+    Measured 1e-6 (contraction length 81) .. 1.1e-5 (length 3 456), growing with the contraction length:
+    the products carry ~2^-21 and the tensor core's fp32 accumulator truncates instead of rounding;
+    cuDNN's CUDA-core fp32 sits at ~1e-6, plain TF32 at ~5e-4."""
+    from deep_attentive_vi_b200 import ops
+    ops.set_conv_precision("3xtf32")
+    torch.manual_seed(ci + co)
+    x = torch.randn(B, HW, HW, ci, device=cuda).permute(0, 3, 1, 2).requires_grad_()
+    w = (torch.randn(co, ci, k, k, device=cuda) / (ci * k * k) ** 0.5).contiguous(
+        memory_format=torch.channels_last).requires_grad_()
+    b = torch.randn(co, device=cuda, requires_grad=True)
+    y = ops.conv2d_bias(x, w, b, stride=stride, padding=pad)
+    go = torch.randn_like(y)
+    g = torch.autograd.grad(y, (x, w, b), go)
+    xd, wd, bd = [t.detach().double().requires_grad_() for t in (x, w, b)]
+    yd = torch.nn.functional.conv2d(xd, wd, bd, stride=stride, padding=pad)
+    gd = torch.autograd.grad(yd, (xd, wd, bd), go.double())
+    err = lambda a, c: ((a.double() - c).abs().max() / c.abs().max()).item()
+    assert err(y, yd) < 2e-5
+    for a, c, name in zip(g, gd, "x w b".split()):
+        assert err(a, c) < 2e-5, (name, err(a, c))
+    assert g[0].is_contiguous(memory_format=torch.channels_last) and g[1].is_contiguous(memory_format=torch.channels_last)
+
+
+def test_conv_bias_gradient_path_matches_autograd(cuda, fp32_convs):
     """ops.conv2d_bias (cuDNN conv + davi_colsum bias gradient) against plain autograd F.conv2d."""
     from deep_attentive_vi_b200 import ops
-    torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
     x = torch.randn(4, 16, 16, 24, device=cuda).permute(0, 3, 1, 2).requires_grad_()
     w = torch.randn(32, 24, 3, 3, device=cuda).contiguous(memory_format=torch.channels_last).requires_grad_()

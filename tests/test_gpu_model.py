@@ -1,6 +1,7 @@
 """Whole-model parity on the GPU: the host model (kernels through the C ABI)
 against the independent fp64 CPU oracle model on the same weights, images and
-noise.  Bar (north_star): ELBO within 1e-4 relative; convs run in full fp32."""
+noise.  Bar (north_star): ELBO within 1e-4 relative.  Every test runs with the host-side convolutions
+in the product default (3xTF32, fp32-grade on the tensor cores) and in cuDNN fp32 (`convs` fixture)."""
 import pytest
 import torch
 
@@ -10,16 +11,10 @@ from oracle.model import OracleVAE
 pytestmark = pytest.mark.gpu
 
 
-def _fp32_exact():
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-
-
-def test_model_without_attention_matches_oracle(cuda):
+def test_model_without_attention_matches_oracle(cuda, convs):
     """The reference's NVAE baseline configuration (README.md:105): no depth-wise attention, no nonlocal
     blocks -- the tensor (not slot-list) branches of encode / call_decoder."""
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
-    _fp32_exact()
     kw = parse_flags(**helpers.SMALL_NVAE)
     torch.manual_seed(0)
     m = DeepVAE(**kw)
@@ -35,9 +30,8 @@ def test_model_without_attention_matches_oracle(cuda):
 
 
 @pytest.mark.parametrize("flags", [helpers.SMALL_CIFAR, helpers.SMALL_OMNIGLOT], ids=["cifar", "omniglot"])
-def test_elbo_and_gradients_match_oracle(cuda, flags):
+def test_elbo_and_gradients_match_oracle(cuda, flags, convs):
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
-    _fp32_exact()
     kw = parse_flags(**flags)
     torch.manual_seed(0)
     m = DeepVAE(**kw)
@@ -73,9 +67,8 @@ def test_elbo_and_gradients_match_oracle(cuda, flags):
         assert err < 1e-3, (k, err.item())
 
 
-def test_importance_sampled_chunk_matches_oracle(cuda):
+def test_importance_sampled_chunk_matches_oracle(cuda, convs):
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
-    _fp32_exact()
     kw = parse_flags(**helpers.SMALL_OMNIGLOT)
     torch.manual_seed(0)
     m = DeepVAE(**kw)
@@ -95,13 +88,12 @@ def test_importance_sampled_chunk_matches_oracle(cuda):
                                          (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz"),
                                          (helpers.SMALL_NVAE, "ref_small_nvae.npz")], ids=["cifar", "omniglot", "nvae"])
 @pytest.mark.parametrize("mode", ["train", "eval"])
-def test_elbo_matches_reference_code_golden(cuda, flags, fname, mode):
+def test_elbo_matches_reference_code_golden(cuda, flags, fname, mode, convs):
     """The CUDA path against the committed output of the reference's OWN DeepVAE.call (executed in
     float64 through tests/golden/tf_shim.py) on the reference's weights, images and random draws.
     Bar: 1e-4 relative on nll, sum(kl) and nelbo (fp32 kernels, fp32 cuDNN convs)."""
     import numpy as np
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
-    _fp32_exact()
     kw = parse_flags(**flags)
     m = DeepVAE(**kw)
     fix, sd = helpers.load_reference_golden(fname, m)
@@ -122,12 +114,11 @@ def test_elbo_matches_reference_code_golden(cuda, flags, fname, mode):
         assert rel < 1e-4, (name, rel)
 
 
-def test_full_omniglot_15_layer_model_matches_oracle(cuda):
+def test_full_omniglot_15_layer_model_matches_oracle(cuda, convs):
     """BASELINE config 0: the published 15-layer OMNIGLOT attentive VAE (7.87 M parameters, README.md:84-96),
     batch 16, synthetic Bernoulli(0.5) 28x28 images padded to 32x32: one ELBO evaluation of the CUDA path
     against the fp64 CPU oracle on the same weights and draws (1e-4 relative)."""
     from deep_attentive_vi_b200.model import OMNIGLOT_15L, DeepVAE, parse_flags
-    _fp32_exact()
     kw = parse_flags(**OMNIGLOT_15L)
     torch.manual_seed(0)
     m = DeepVAE(**kw)

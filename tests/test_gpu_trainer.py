@@ -36,13 +36,11 @@ def test_adamax_matches_keras_rule(cuda):
     assert (p.double().cpu() - pr).abs().max() < 1e-5
 
 
-def test_graph_replay_equals_eager_step(cuda):
+def test_graph_replay_equals_eager_step(cuda, convs):
     """Same weights, images and (fixed) noise: 3 eager warm-up steps + 3 graph
     replays must equal 6 eager steps."""
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
     from deep_attentive_vi_b200.util.trainer import Trainer
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.deterministic = True
     kw = parse_flags(**helpers.SMALL_CIFAR)
@@ -73,14 +71,12 @@ def test_graph_replay_equals_eager_step(cuda):
     assert (p0 - p1).abs().max().item() < 1e-3
 
 
-def test_fused_weight_norm_matches_per_layer_path(cuda):
+def test_fused_weight_norm_matches_per_layer_path(cuda, convs):
     """davi_weight_norm_fwd/bwd (all conv kernels in one launch over the flat parameter array)
     against the per-layer torch restatement of layers/weight_norm.py:126-135: same loss, same
     gradients of every v and log_g."""
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
     from deep_attentive_vi_b200.util.trainer import Trainer
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.deterministic = True
     kw = parse_flags(**helpers.SMALL_CIFAR)

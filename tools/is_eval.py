@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deep_attentive_vi_b200 import ops  # noqa: E402
 from deep_attentive_vi_b200.model import CIFAR10_16L, DeepVAE, parse_flags  # noqa: E402
 from deep_attentive_vi_b200.util.eval import GraphedChunks, importance_log_likelihood  # noqa: E402
 
@@ -36,8 +37,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.allow_tf32 = True
-    torch.backends.cuda.matmul.allow_tf32 = True
+    ops.set_conv_precision(os.environ.get("CONVS", "3xtf32"))
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)                                      # same weights on every rank
     model = DeepVAE(**parse_flags(**CIFAR10_16L)).to(dev).eval()

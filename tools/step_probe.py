@@ -9,9 +9,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deep_attentive_vi_b200.model import CIFAR10_16L, DeepVAE, parse_flags  # noqa: E402
 
-tf32 = os.environ.get("TF32", "1") == "1"
-torch.backends.cudnn.allow_tf32 = tf32
-torch.backends.cuda.matmul.allow_tf32 = tf32
+from deep_attentive_vi_b200 import ops  # noqa: E402
+tf32 = os.environ.get("CONVS", "3xtf32")        # 3xtf32 (default) | fp32 | tf32
+ops.set_conv_precision(tf32)
 torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda")
 torch.manual_seed(0)
@@ -37,7 +37,7 @@ for _ in range(n):
     step()
 torch.cuda.synchronize()
 dt = (time.time() - t) / n
-print(f"step {dt*1e3:.1f} ms  -> {B/dt:.1f} img/s (tf32={tf32}), mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
+print(f"step {dt*1e3:.1f} ms  -> {B/dt:.1f} img/s (convs={tf32}), mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
 from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()

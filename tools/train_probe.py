@@ -7,8 +7,7 @@ from deep_attentive_vi_b200.util.trainer import Trainer
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = torch.device("cuda")
-torch.backends.cudnn.allow_tf32 = True
-torch.backends.cuda.matmul.allow_tf32 = True
+from deep_attentive_vi_b200 import ops as _ops; _ops.set_conv_precision(os.environ.get("CONVS", "3xtf32"))
 torch.backends.cudnn.benchmark = True
 for use_graph in (False, True):
     torch.manual_seed(0)
