@@ -305,7 +305,7 @@ def run_davi(args):
     ms, ms_e2e, launches, clocks, nparams = r["ms"], r["ms_e2e"], r["launches"], r["clocks"], r["params"]
     last = {"loss": r["loss"]}
     alt = None
-    if args.alt_convs and args.alt_convs != args.convs:
+    if args.alt_convs and args.alt_convs != args.convs and world == 1:   # second trainer + graph: one GPU only
         alt = measure(args.alt_convs)
 
     value = B * world * args.steps / (ms / 1e3)

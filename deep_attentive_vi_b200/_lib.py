@@ -47,6 +47,7 @@ SIGNATURES = {
     "davi_colsum": (_i, [_f, _f, _l, _i, _l, _f, _z, _s]),
     "davi_multi_copy": (_i, [_pp, _lp, _lp, _i, _f, _s]),
     "davi_split_tf32": (_i, [_f, _f, _l, _i, _i, _i, _s]),
+    "davi_split_tf32_dual": (_i, [_f, _f, _f, _l, _i, _i, _i, _s]),
     "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
     "davi_adamax_step_dev": (_i, [_f, _f, _f, _f, _l, _f, _r, _r, _r, _r, _s]),
 }

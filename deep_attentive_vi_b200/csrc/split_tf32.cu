@@ -69,9 +69,55 @@ split_tf32_scalar_kernel(const float* __restrict__ src, float* __restrict__ dst,
     }
 }
 
+// Both layouts from one read of src: dst_ch [rows, 3C] with part order `pat_ch`, dst_pl [3, rows, C] with
+// `pat_pl` (an activation feeds the forward conv in one layout and the weight gradient in the other; an
+// output gradient feeds the input gradient and the weight gradient).
+__global__ void __launch_bounds__(kSplitThreads)
+split_tf32_dual_vec_kernel(const float* __restrict__ src, float* __restrict__ dst_ch, float* __restrict__ dst_pl,
+                           int64_t n4, int C4, int pat_ch, int pat_pl) {
+    const int64_t C = 4 * (int64_t)C4, n = 4 * n4;
+    for (int64_t i = (int64_t)blockIdx.x * kSplitThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kSplitThreads) {
+        const int64_t r = i / C4;
+        const int c = (int)(i - r * C4) * 4;
+        const float4 v = ld_stream4(src + 4 * i);
+        float4 hi, lo;
+        hi.x = rna_tf32(v.x); lo.x = rna_tf32(v.x - hi.x);
+        hi.y = rna_tf32(v.y); lo.y = rna_tf32(v.y - hi.y);
+        hi.z = rna_tf32(v.z); lo.z = rna_tf32(v.z - hi.z);
+        hi.w = rna_tf32(v.w); lo.w = rna_tf32(v.w - hi.w);
+        float* o = dst_ch + r * 3 * C + c;
+        *reinterpret_cast<float4*>(o) = hi;
+        *reinterpret_cast<float4*>(o + C) = pat_ch == 0 ? lo : hi;
+        *reinterpret_cast<float4*>(o + 2 * C) = pat_ch == 0 ? hi : lo;
+        float* q = dst_pl + 4 * i;
+        *reinterpret_cast<float4*>(q) = hi;
+        *reinterpret_cast<float4*>(q + n) = pat_pl == 0 ? lo : hi;
+        *reinterpret_cast<float4*>(q + 2 * n) = pat_pl == 0 ? hi : lo;
+    }
+}
+
 }  // namespace davi
 
 using namespace davi;
+
+extern "C" int davi_split_tf32_dual(const float* src, float* dst_ch, float* dst_pl, int64_t rows, int C,
+                                    int pattern_ch, int pattern_pl, davi_stream_t stream) {
+    DAVI_REQUIRE(src && dst_ch && dst_pl, "null pointer");
+    DAVI_REQUIRE(rows > 0 && C > 0, "empty tensor");
+    DAVI_REQUIRE((pattern_ch == 0 || pattern_ch == 1) && (pattern_pl == 0 || pattern_pl == 1), "pattern");
+    if (C % 4 == 0 && aligned16(src) && aligned16(dst_ch) && aligned16(dst_pl)) {
+        const int64_t n4 = rows * C / 4;
+        int64_t blocks = (n4 + kSplitThreads - 1) / kSplitThreads;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        split_tf32_dual_vec_kernel<<<(unsigned)blocks, kSplitThreads, 0, (cudaStream_t)stream>>>(
+            src, dst_ch, dst_pl, n4, C / 4, pattern_ch, pattern_pl);
+        return check_launch(__func__);
+    }
+    int rc = davi_split_tf32(src, dst_ch, rows, C, 0, pattern_ch, stream);      // odd channel counts: two launches
+    if (rc) return rc;
+    return davi_split_tf32(src, dst_pl, rows, C, 1, pattern_pl, stream);
+}
+
 
 extern "C" int davi_split_tf32(const float* src, float* dst, int64_t rows, int C, int layout, int pattern,
                                davi_stream_t stream) {

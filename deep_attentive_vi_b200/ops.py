@@ -668,36 +668,67 @@ def split_tf32(t, layout, pattern):
     return out
 
 
+def split_tf32_dual(t, pattern_ch, pattern_pl):
+    """Both layouts of split_tf32 from one read of t (NCHW-shaped, channels_last memory)."""
+    _require_cuda(t)
+    nhwc = t.permute(0, 2, 3, 1)
+    if not nhwc.is_contiguous():
+        nhwc = nhwc.contiguous()
+    B, H, W, C = nhwc.shape
+    ch = torch.empty((B, H, W, 3 * C), device=t.device, dtype=torch.float32)
+    pl = torch.empty((3 * B, H, W, C), device=t.device, dtype=torch.float32)
+    _lib_call("davi_split_tf32_dual", _p(nhwc), _p(ch), _p(pl), B * H * W, C, pattern_ch, pattern_pl, _stream())
+    return ch.permute(0, 3, 1, 2), pl.permute(0, 3, 1, 2)
+
+
 class _ConvBias3x(torch.autograd.Function):
-    """fp32-grade convolution on the TF32 tensor cores.  With a = hi_a + lo_a (davi_split_tf32):
+    """fp32-grade convolution on the TF32 tensor cores.  With a ~= hi_a + lo_a (davi_split_tf32):
         y  = conv([x_hi | x_lo | x_hi], [w_hi | w_hi | w_lo])            contraction over 3 * C_in
         gx = conv_input([gy_hi | gy_lo | gy_hi], [w_hi ; w_hi ; w_lo])   contraction over 3 * C_out
         gw = conv_weight([x_hi ; x_lo ; x_hi], [gy_hi ; gy_hi ; gy_lo])  contraction over 3 * batch
-    each ONE cuDNN TF32 call with fp32 accumulation (hi parts are exact in TF32, lo parts carry the
-    next 11+ bits)."""
+    each ONE cuDNN TF32 call with fp32 accumulation (both parts are exact in TF32; lo carries the next
+    11 bits).  One split kernel per tensor writes the layout the forward needs and the one the backward
+    needs; the backward layouts are what is saved."""
 
     @staticmethod
     def forward(ctx, x, w, b, stride, padding):
-        ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding)
-        return torch.nn.functional.conv2d(split_tf32(x, 0, 0), split_tf32(w, 0, 1), b, stride=stride, padding=padding)
+        need_gx, need_gw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_gw:
+            x3, x3p = split_tf32_dual(x, 0, 0)
+        else:
+            x3, x3p = split_tf32(x, 0, 0), None
+        if need_gx:
+            w3, w3p = split_tf32_dual(w, 1, 1)
+        else:
+            w3, w3p = split_tf32(w, 0, 1), None
+        ctx.save_for_backward(x3p, w3p)
+        ctx.shapes = (x.shape, w.shape)
+        return torch.nn.functional.conv2d(x3, w3, b, stride=stride, padding=padding)
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        stride, padding = ctx.cfg
+        x3p, w3p = ctx.saved_tensors
+        (xs, ws), (stride, padding) = ctx.shapes, ctx.cfg
         s = (stride, stride) if isinstance(stride, int) else tuple(stride)
         p = (padding, padding) if isinstance(padding, int) else tuple(padding)
+        need_gx, need_gw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gx = gw = gb = None
+        if need_gx and need_gw:
+            gy3, gy3p = split_tf32_dual(gy, 0, 1)
+        else:
+            gy3 = split_tf32(gy, 0, 0) if need_gx else None
+            gy3p = split_tf32(gy, 1, 1) if need_gw else None
         # aten.convolution_backward takes shape and memory format of the result from its `input` / `weight`
-        # argument: passing x and w themselves keeps both gradients channels_last (no layout copies)
-        if ctx.needs_input_grad[0]:
-            w3 = split_tf32(w, 1, 1)
-            gx = torch.ops.aten.convolution_backward(split_tf32(gy, 0, 0), x, w3, [w3.shape[0]], s, p, (1, 1), False,
+        # argument: one plane of the saved split (same shape and channels_last layout as x / w) serves
+        if need_gx:
+            like_x = x3p[:xs[0]] if x3p is not None else torch.empty(xs, device=gy.device, dtype=gy.dtype, memory_format=torch.channels_last)
+            gx = torch.ops.aten.convolution_backward(gy3, like_x, w3p, [w3p.shape[0]], s, p, (1, 1), False,
                                                      (0, 0), 1, (True, False, False))[0]
-        if ctx.needs_input_grad[1]:
-            gw = torch.ops.aten.convolution_backward(split_tf32(gy, 1, 1), split_tf32(x, 1, 0), w, [w.shape[0]], s, p,
-                                                     (1, 1), False, (0, 0), 1, (False, True, False))[1]
+        if need_gw:
+            like_w = w3p[:ws[0]] if w3p is not None else torch.empty(ws, device=gy.device, dtype=gy.dtype, memory_format=torch.channels_last)
+            gw = torch.ops.aten.convolution_backward(gy3p, x3p, like_w, [ws[0]], s, p, (1, 1), False, (0, 0), 1,
+                                                     (False, True, False))[1]
         if ctx.needs_input_grad[2]:
             gb = colsum_nhwc(gy)
         return gx, gw, gb, None, None

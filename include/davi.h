@@ -325,6 +325,9 @@ int davi_multi_copy(const float* const* srcs, const int64_t* dst_offsets, const 
  * (layers/resnet.py:589-601) to ~2^-21 per product. */
 int davi_split_tf32(const float* src, float* dst, int64_t rows, int C, int layout, int pattern,
                     davi_stream_t stream);
+/* Both layouts from one read: dst_ch = layout 0 with pattern_ch, dst_pl = layout 1 with pattern_pl. */
+int davi_split_tf32_dual(const float* src, float* dst_ch, float* dst_pl, int64_t rows, int C,
+                         int pattern_ch, int pattern_pl, davi_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -291,6 +291,12 @@ def test_split_tf32_parts_are_exact(cuda):
                 assert int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
                 assert ((hi.double() + lo.double() - v.double()).abs() <= v.abs().double() * 2.0 ** -21).all()
                 assert ((lo.abs() <= hi.abs() * 2.0 ** -10) | (hi == 0)).all()
+    # one read, both layouts: identical to the two single-layout calls (vector path and odd-C path)
+    for C in (24, 3):
+        t = torch.randn(5, 7, 6, C, device=cuda).permute(0, 3, 1, 2)
+        for pc, pp in ((0, 0), (0, 1), (1, 1)):
+            ch, pl = ops.split_tf32_dual(t, pc, pp)
+            assert torch.equal(ch, ops.split_tf32(t, 0, pc)) and torch.equal(pl, ops.split_tf32(t, 1, pp))
 
 
 @pytest.mark.parametrize("B,HW,ci,co,k,stride,pad", [(4, 16, 24, 32, 3, 1, 1), (3, 32, 3, 32, 3, 1, 1),
