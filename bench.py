@@ -209,6 +209,69 @@ def dw_roofline(batch, device):
     return tot_b, tot_t, per_call
 
 
+def nl_roofline(shapes, device):
+    """Tensor-pipe view of the model's nonlocal attention calls (`shapes`: one (B, N, d, C) per call of a
+    step, recorded by forward hooks).  Algorithmic flops -- forward 2 B N^2 (d + C), backward
+    2 B N^2 (2 C + 3 d): the five GEMMs of the gradient plus one recomputation of S -- over the CUDA-event
+    time of the C-ABI calls, each shape launched back to back on rotating operand sets with a footprint
+    above 3x L2.  The kernels execute 3 tcgen05 TF32 MMAs per algorithmic product (3xTF32)."""
+    import collections
+    import torch
+    from deep_attentive_vi_b200 import _lib
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    scale, gamma = torch.tensor(0.8, device=device), torch.tensor(0.6, device=device)
+    tot_f = tot_t = 0.0
+    per_shape = []
+    for (B, N, d, C), count in sorted(collections.Counter(shapes).items()):
+        rs = 2 * d + C
+        per_set = 4 * B * N * (2 * rs + 4 * C)
+        sets = max(2, min(12, int(3 * 126e6 // per_set) + 1))
+        qkv = [torch.randn(B, N, rs, device=device) * 0.5 for _ in range(sets)]
+        x = [torch.randn(B, N, C, device=device) for _ in range(sets)]
+        go = [torch.randn(B, N, C, device=device) for _ in range(sets)]
+        y = [torch.empty(B, N, C, device=device) for _ in range(sets)]
+        o = [torch.empty(B, N, C, device=device) for _ in range(sets)]
+        lse = [torch.empty(B, N, device=device) for _ in range(sets)]
+        dqkv = [torch.empty(B, N, rs, device=device) for _ in range(2)]
+        dgs = torch.empty(2, device=device)
+        wsb = lib.davi_nonlocal_attn_bwd_workspace_bytes(B, N, d, C)
+        ws = torch.empty(max(wsb // 4, 1), device=device)
+
+        def fwd(i):
+            q = qkv[i].data_ptr()
+            _lib.call("davi_nonlocal_attn_fwd", q, q + 4 * d, q + 8 * d, x[i].data_ptr(), y[i].data_ptr(),
+                      lse[i].data_ptr(), o[i].data_ptr(), B, N, d, C, rs, rs, rs, C, C, C, scale.data_ptr(),
+                      gamma.data_ptr(), stream)
+
+        def bwd(i):
+            q, dq = qkv[i].data_ptr(), dqkv[i % 2].data_ptr()
+            _lib.call("davi_nonlocal_attn_bwd", q, q + 4 * d, q + 8 * d, lse[i].data_ptr(), o[i].data_ptr(),
+                      go[i].data_ptr(), dq, dq + 4 * d, dq + 8 * d, dgs.data_ptr(), B, N, d, C, rs, rs, rs, C, C,
+                      scale.data_ptr(), gamma.data_ptr(), ws.data_ptr(), wsb, stream)
+
+        flops = {"fwd": 2.0 * B * N * N * (d + C), "bwd": 2.0 * B * N * N * (2 * C + 3 * d)}
+        for name, fn in (("fwd", fwd), ("bwd", bwd)):
+            for i in range(sets):
+                fn(i)                                   # forward first: the backward reads lse / o of its set
+            ts = []
+            for rep in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(sets):
+                    fn(i)
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1) / sets)
+            t = sorted(ts)[1]
+            tot_f += count * flops[name]
+            tot_t += count * t
+            per_shape.append({"k": name, "B": B, "N": N, "d": d, "C": C, "calls": count, "us": round(t * 1e3, 1),
+                              "TFLOPs": round(flops[name] / t / 1e9, 1)})
+        del qkv, x, go, y, o, lse, dqkv
+    return tot_f, tot_t, per_shape
+
+
 # ---------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------
@@ -284,8 +347,18 @@ def run_davi(args):
             nll, kl = trainer.train_step(x)
             last["loss"] = float((nll.mean() + kl.mean()).item())      # D2H read of the step's loss
 
+        from deep_attentive_vi_b200.layers.attention import NonlocalResNetBlock
+        nl_shapes, hooks = [], []
+        for mod in model.modules():
+            if isinstance(mod, NonlocalResNetBlock):
+                hooks.append(mod.register_forward_hook(
+                    lambda m_, inp, out_: nl_shapes.append((inp[0].shape[0], inp[0].shape[1] * inp[0].shape[2],
+                                                            m_._key_dim, inp[0].shape[3]))))
         for s in range(args.warmup):
             resident_step(s)
+            for h in hooks:                                          # shapes of ONE step; no hooks under capture
+                h.remove()
+            hooks = []
         if sampler is not None:
             sampler.start()
         calls0 = _lib.launch_count()
@@ -296,7 +369,7 @@ def run_davi(args):
         ms_e2e = timed(e2e_step, args.steps)
         clocks = sampler.stop() if sampler is not None else None
         out = {"ms": ms, "ms_e2e": ms_e2e, "launches": launches, "loss": last.get("loss"), "clocks": clocks,
-               "params": model.count_params()}
+               "params": model.count_params(), "nl_shapes": nl_shapes}
         del trainer, model
         torch.cuda.empty_cache()
         return out
@@ -344,6 +417,22 @@ def run_davi(args):
                                                    "bwd_algorithmic_MB": 376.7,
                                                    "note": "bwd writes partly still in L2 at kernel end"},
                                 "algorithmic_MB_per_step": tb / 1e6, "kernel_ms_per_step": tt}
+            tf, tt_nl, per_shape = nl_roofline(r["nl_shapes"], device)
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    tf32_peak, tf32_src = float(json.load(f)["bf16_tflops"]) / 2, \
+                        "half of the measured bf16 burst peak (MEASURED_PEAKS.json bf16_tflops; TF32 runs at half the bf16 rate)"
+            except Exception:
+                tf32_peak, tf32_src = 1125.0, "fallback: nominal dense TF32 (half of 2.25 PF bf16)"
+            ach_tf = tf / tt_nl / 1e9
+            line["roofline_nonlocal"] = {
+                "bound": "tensor", "kernel": f"nonlocal attention fwd + bwd ({len(r['nl_shapes'])} calls of one step)",
+                "achieved": ach_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach_tf / tf32_peak,
+                "executed_frac": 3 * ach_tf / tf32_peak, "peak_source": tf32_src,
+                "note": "achieved = algorithmic flops / CUDA-event time; the kernels execute 3 TF32 MMAs per product "
+                        "(3xTF32 error compensation, fp32-grade), so the tensor pipe runs at executed_frac; "
+                        "ncu: profiles/r01_ncu_nonlocal_tc_v4_summary.txt",
+                "kernel_ms_per_step": tt_nl, "per_shape": per_shape}
             if args.roofline_detail:
                 with open(args.roofline_detail, "w") as f:
                     json.dump(per_call, f)
