@@ -223,7 +223,8 @@ def nl_roofline(shapes, device):
     scale, gamma = torch.tensor(0.8, device=device), torch.tensor(0.6, device=device)
     tot_f = tot_t = 0.0
     per_shape = []
-    for (B, N, d, C), count in sorted(collections.Counter(shapes).items()):
+    for (B, N, d, C_alg), count in sorted(collections.Counter(shapes).items()):
+        C = C_alg + (-C_alg) % 4          # the layer zero-pads odd channel counts (C = 138 in the pre-processor)
         rs = 2 * d + C
         per_set = 4 * B * N * (2 * rs + 4 * C)
         sets = max(2, min(12, int(3 * 126e6 // per_set) + 1))
@@ -250,7 +251,7 @@ def nl_roofline(shapes, device):
                       go[i].data_ptr(), dq, dq + 4 * d, dq + 8 * d, dgs.data_ptr(), B, N, d, C, rs, rs, rs, C, C,
                       scale.data_ptr(), gamma.data_ptr(), ws.data_ptr(), wsb, stream)
 
-        flops = {"fwd": 2.0 * B * N * N * (d + C), "bwd": 2.0 * B * N * N * (2 * C + 3 * d)}
+        flops = {"fwd": 2.0 * B * N * N * (d + C_alg), "bwd": 2.0 * B * N * N * (2 * C_alg + 3 * d)}
         for name, fn in (("fwd", fwd), ("bwd", bwd)):
             for i in range(sets):
                 fn(i)                                   # forward first: the backward reads lse / o of its set
@@ -266,7 +267,7 @@ def nl_roofline(shapes, device):
             t = sorted(ts)[1]
             tot_f += count * flops[name]
             tot_t += count * t
-            per_shape.append({"k": name, "B": B, "N": N, "d": d, "C": C, "calls": count, "us": round(t * 1e3, 1),
+            per_shape.append({"k": name, "B": B, "N": N, "d": d, "C": C_alg, "calls": count, "us": round(t * 1e3, 1),
                               "TFLOPs": round(flops[name] / t / 1e9, 1)})
         del qkv, x, go, y, o, lse, dqkv
     return tot_f, tot_t, per_shape
