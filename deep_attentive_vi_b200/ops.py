@@ -713,7 +713,8 @@ class _ConvBias3x(torch.autograd.Function):
         s = (stride, stride) if isinstance(stride, int) else tuple(stride)
         p = (padding, padding) if isinstance(padding, int) else tuple(padding)
         need_gx, need_gw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gx = gw = gb = None
+        gx = gw = None
+        gb = colsum_nhwc(gy) if ctx.needs_input_grad[2] else None      # first: gy is still L2-resident
         if need_gx and need_gw:
             gy3, gy3p = split_tf32_dual(gy, 0, 1)
         else:
@@ -729,8 +730,6 @@ class _ConvBias3x(torch.autograd.Function):
             like_w = w3p[:ws[0]] if w3p is not None else torch.empty(ws, device=gy.device, dtype=gy.dtype, memory_format=torch.channels_last)
             gw = torch.ops.aten.convolution_backward(gy3p, x3p, like_w, [ws[0]], s, p, (1, 1), False, (0, 0), 1,
                                                      (False, True, False))[1]
-        if ctx.needs_input_grad[2]:
-            gb = colsum_nhwc(gy)
         return gx, gw, gb, None, None
 
 

@@ -63,6 +63,7 @@ def main():
                           "value": args.samples * args.batch / sec, "unit": "sample-images/s", "n_gpus": world,
                           "seconds_per_batch": sec, "num_importance_samples": args.samples, "batch": args.batch,
                           "chunk": args.chunk, "sharding": "by sample", "cuda_graph": not args.eager, "data": "synthetic",
+                          "convs": ops.get_conv_precision(),
                           "mean_log_likelihood_nats": float(logp.mean().item())}), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local])
