@@ -98,3 +98,22 @@ def test_data_parallel_and_sample_sharding_with_gloo():
         mp.spawn(_dp_worker, args=(world, port, ret), nprocs=world, join=True)
         assert ret["dp_err"] < 1e-10
         assert ret["is_err"] < 1e-10
+
+
+def test_conv_precision_modes_are_validated():
+    """ops.set_conv_precision: three named modes (default = fp32-grade 3xTF32); anything else is an error,
+    and the mode sets torch's cuDNN TF32 switch the way the mode needs it."""
+    import pytest
+    import torch
+    from deep_attentive_vi_b200 import ops
+    assert ops.get_conv_precision() == "3xtf32"
+    try:
+        ops.set_conv_precision("fp32")
+        assert ops.get_conv_precision() == "fp32" and not torch.backends.cudnn.allow_tf32
+        ops.set_conv_precision("tf32")
+        assert torch.backends.cudnn.allow_tf32 and torch.backends.cuda.matmul.allow_tf32
+        with pytest.raises(ValueError):
+            ops.set_conv_precision("bf16")
+    finally:
+        ops.set_conv_precision("3xtf32")
+    assert torch.backends.cudnn.allow_tf32 and not torch.backends.cuda.matmul.allow_tf32

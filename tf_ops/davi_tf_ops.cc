@@ -341,3 +341,41 @@ class DaviBernoulliNllOp : public OpKernel {
   int crop_;
 };
 REGISTER_KERNEL_BUILDER(Name("DaviBernoulliNll").Device(tf::DEVICE_GPU), DaviBernoulliNllOp);
+
+// ---------------------------------------------------------------------------
+// DaviSplitTf32: three-part TF32 operand split for fp32-grade Conv2D on the tensor cores
+// (row f1; src/layers/resnet.py:589-601, src/layers/weight_norm.py:126-135)
+//   x [..., C] -> layout 0: [..., 3C] ; layout 1: [3 * dim0, ..., C]
+// ---------------------------------------------------------------------------
+REGISTER_OP("DaviSplitTf32")
+    .Input("x: float")
+    .Attr("layout: int = 0").Attr("pattern: int = 0")
+    .Output("parts: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->UnknownShape());
+      return tf::Status::OK();
+    });
+
+class DaviSplitTf32Op : public OpKernel {
+ public:
+  explicit DaviSplitTf32Op(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("layout", &layout_));
+    OP_REQUIRES_OK(c, c->GetAttr("pattern", &pattern_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& x = ctx->input(0);
+    const int nd = x.dims();
+    OP_REQUIRES(ctx, nd >= 1, tf::errors::InvalidArgument("DaviSplitTf32: rank >= 1"));
+    const int C = x.dim_size(nd - 1);
+    const tf::int64 rows = x.NumElements() / C;
+    TensorShape shape = x.shape();
+    if (layout_ == 0) shape.set_dim(nd - 1, 3 * C); else shape.set_dim(0, 3 * x.dim_size(0));
+    Tensor* out;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, shape, &out));
+    OP_REQUIRES_OK(ctx, Check(davi_split_tf32(P(x), P(out), rows, C, layout_, pattern_, StreamOf(ctx)),
+                              "davi_split_tf32"));
+  }
+ private:
+  int layout_, pattern_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviSplitTf32").Device(tf::DEVICE_GPU), DaviSplitTf32Op);
