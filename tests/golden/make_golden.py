@@ -12,7 +12,8 @@ Outputs (committed):
   ref_small_cifar.npz    whole-model [nll, kl, nelbo] of DeepVAE.call for a 4-layer CIFAR-like
   ref_small_omniglot.npz config / a 3-layer OMNIGLOT-like config / a 3-layer NVAE-like config without
   ref_small_nvae.npz     attention: weights (by reference attribute path), input batch, every random
-                         draw in call order, outputs
+                         draw in call order, outputs; plus one chunk of the importance-sampled
+                         estimator (DeepVAE.infer_worker_body, 3 samples per image) with its draws
 What this pins: the reference's Python logic (reshape scrambles, channel maps, stack/split order,
 LN placement, residual parametrisation, loss assembly).  What it assumes: the TF/TFP/tfa kernels
 behave as tf_shim.py restates them (documented semantics of the pinned versions).
@@ -113,6 +114,15 @@ def model_case(flags, fname, batch, seed):
         out[f"{mode}/nll"], out[f"{mode}/kl"], out[f"{mode}/nelbo"] = nll.numpy(), kl.numpy(), nelbo.numpy()
         for i, (tag, z) in enumerate(tf_shim.REC.normal_draws):
             out[f"{mode}/draw/{i:03d}/{tag}"] = z.numpy()
+    # R10: one worker chunk of the importance-sampled estimator (vae.py:452-482) with S = 3 samples per image:
+    # tiled batch (index = s * B + b), per-layer log p - log q, minus nll, logsumexp over the samples
+    S = 3
+    tf_shim.REC.normal_draws.clear()
+    tf_shim.REC.training_noise = False
+    out["is/num_samples"] = np.int64(S)
+    out["is/logsumexp"] = m.infer_worker_body(x, S).numpy()
+    for i, (tag, z) in enumerate(tf_shim.REC.normal_draws):
+        out[f"is/draw/{i:03d}/{tag}"] = z.numpy()
     out["x"] = x.numpy()
     for path, name, w, _, _ in tf_shim.walk_weights(m):
         if name == "initialized":

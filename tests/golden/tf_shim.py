@@ -535,6 +535,13 @@ class Layer(Module):
                 shp = None
             self.build(shp)
             self.built = True
+        if "training" in kwargs:
+            # Keras base_layer.__call__: a `training` keyword is dropped when call() does not take one
+            # (the reference relies on it: vae.py:468 passes training=False to ConcatConv2D.call(inputs))
+            import inspect
+            ps = inspect.signature(self.call).parameters
+            if "training" not in ps and not any(p.kind == p.VAR_KEYWORD for p in ps.values()):
+                kwargs.pop("training")
         return self.call(inputs, *args, **kwargs)
 
     def call(self, inputs, *a, **k):

@@ -174,3 +174,10 @@ def golden_noise(fix, mode, L, training_noise):
         noise.append((qn, pn))
     assert next(it, None) is None
     return eps, (noise if training_noise else None)
+
+
+def golden_is_draws(fix):
+    """The recorded eps draws of the importance-sampled chunk (one [S*B,H,W,z] tensor per layer, in call order)."""
+    keys = sorted(k for k in fix if k.startswith("is/draw/"))
+    assert all(k.endswith("mvn_sample") for k in keys)
+    return [torch.from_numpy(fix[k])[0] for k in keys]

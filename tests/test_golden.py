@@ -73,3 +73,22 @@ def test_whole_model_elbo_matches_reference_code(flags, fname, mode):
         want = torch.from_numpy(fix[f"{mode}/{name}"])
         rel = ((got - want).abs() / want.abs()).max().item()
         assert rel < 1e-9, (name, rel, got, want)
+
+
+@pytest.mark.parametrize("flags,fname", [(helpers.SMALL_CIFAR, "ref_small_cifar.npz"),
+                                         (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz"),
+                                         (helpers.SMALL_NVAE, "ref_small_nvae.npz")])
+def test_importance_sampled_chunk_matches_reference_code(flags, fname):
+    """One worker chunk of the importance-sampled estimator (DeepVAE.infer_worker_body, vae.py:452-482:
+    sample-major tiling, per-layer log p - log q, minus nll, logsumexp over the samples) executed by the
+    reference's own code on its weights and recorded draws."""
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    kw = parse_flags(**flags)
+    model = DeepVAE(**kw)
+    fix, sd = helpers.load_reference_golden(fname, model)
+    eps = helpers.golden_is_draws(fix)
+    assert len(eps) == kw["hparams"].num_layers
+    o = OracleVAE(helpers.oracle_cfg(kw), sd, dtype=torch.float64)
+    got = o.is_chunk(torch.from_numpy(fix["x"]), eps, int(fix["is/num_samples"]))
+    want = torch.from_numpy(fix["is/logsumexp"])
+    assert ((got - want).abs() / want.abs()).max().item() < 1e-9, (got, want)

@@ -114,6 +114,24 @@ def test_elbo_matches_reference_code_golden(cuda, flags, fname, mode, convs):
         assert rel < 1e-4, (name, rel)
 
 
+@pytest.mark.parametrize("flags,fname", [(helpers.SMALL_CIFAR, "ref_small_cifar.npz"),
+                                         (helpers.SMALL_OMNIGLOT, "ref_small_omniglot.npz")], ids=["cifar", "omniglot"])
+def test_importance_chunk_matches_reference_code_golden(cuda, flags, fname, convs):
+    """DeepVAE.infer_worker_body on the GPU (log q / log p kernels, NLL kernels, davi_is_logsumexp) against the
+    committed output of the reference's own infer_worker_body (vae.py:452-482) on its weights and draws."""
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    kw = parse_flags(**flags)
+    m = DeepVAE(**kw)
+    fix, sd = helpers.load_reference_golden(fname, m)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    eps = [e.float().to(cuda) for e in helpers.golden_is_draws(fix)]
+    with torch.no_grad():
+        got = m.infer_worker_body(torch.from_numpy(fix["x"]).float().to(cuda), int(fix["is/num_samples"]), eps=eps)
+    want = torch.from_numpy(fix["is/logsumexp"])
+    assert ((got.double().cpu() - want).abs() / want.abs()).max().item() < 1e-4
+
+
 def test_full_omniglot_15_layer_model_matches_oracle(cuda, convs):
     """BASELINE config 0: the published 15-layer OMNIGLOT attentive VAE (7.87 M parameters, README.md:84-96),
     batch 16, synthetic Bernoulli(0.5) 28x28 images padded to 32x32: one ELBO evaluation of the CUDA path
