@@ -13,7 +13,12 @@ in HBM; `e2e` repeats the measurement through the public API with pinned-host
 inputs copied H2D every step and the step's loss read back D2H.
 `roofline` reports the depth-wise attention kernels (the memory-bound hot kernel
 north_star names): algorithmic bytes / CUDA-event time of the model's 31 forward
-+ 31 backward calls at this batch size, each timed alone after an L2 flush.
++ 31 backward calls at this batch size, launched back to back on rotating operand
+sets larger than L2.  `roofline_nonlocal` is the tensor-bound view of the 128
+nonlocal attention calls.  Precision: the hot-path kernels compute in fp32 (3xTF32
+on the tensor cores); the host-side cuDNN convolutions run in 3xTF32 by default
+(`--convs`), and the opt-in plain-TF32 step is measured into `alt_convs` for the
+record (one GPU only).
 """
 import argparse
 import json
