@@ -20,8 +20,10 @@
 // passes over the column blocks (row max first; then exp, row sum and P*V with
 // unnormalised P, divided by the row sum in the epilogue), so the accumulator is
 // never rescaled.  TMEM columns: S [0,128) | O [128,128+Cp) | P ring [448,512).
-// Instruction cost measured by tools/umma_probe2.cu (profiles/r01_umma_probe2.txt):
-// ~173 cycles per SS MMA, ~115 per TS MMA, independent of N <= 160.
+// Issue rates: tools/umma_probe2.cu measured ~173 (SS) / ~115 (TS) cycles per MMA for ITS issue loop, which
+// rebuilds both descriptors from a parameter struct every iteration; tools/umma_probe3.cu, with descriptors
+// advanced by one add, issues at the tensor pipe's own rate (CTA pair, M = 256: 45 / 64 / 128 cycles at
+// N = 64 / 128 / 256 = 4096 flop/cycle/SM).  The kernels below advance descriptor low words by one add.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -282,7 +284,8 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
             const uint32_t idesc_s = idesc_tf32(kPvM, kPvKB, false, false);
             const uint32_t idesc_o1 = idesc_tf32(kPvM, g.n1, false, true);
             const uint32_t idesc_o2 = idesc_tf32(kPvM, g.n2 > 0 ? g.n2 : 32, false, true);
-            const uint32_t aXr = smem_u32(sXr), aXl = smem_u32(sXl);
+            // operands are tracked as descriptor LOW WORDS (start address >> 4 | LBO): advancing one is a single add
+            const uint32_t aXr = kmajor_lo(smem_u32(sXr)), aXl = kmajor_lo(smem_u32(sXl));
             uint32_t n_s = 0;
             auto issue_s = [&](int u) {
                 const int buf = u & 1;
@@ -291,12 +294,12 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                 if (n_s > 0) mbar_wait(&bars.s_empty, (n_s - 1) & 1);
                 ++n_s;
                 tc_fence_after();
-                const uint32_t aYr = smem_u32(sYr(buf)), aYl = smem_u32(sYl(buf));
+                const uint32_t aYr = kmajor_lo(smem_u32(sYr(buf))), aYl = kmajor_lo(smem_u32(sYl(buf)));
                 for (int ks = 0; ks < g.ksteps; ++ks) {
-                    const uint32_t o = ks * 32;
-                    mma_tf32(tmem, desc_kmajor(aXl + o), desc_kmajor(aYr + o), idesc_s, ks > 0);
-                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYl + o), idesc_s, true);
-                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYr + o), idesc_s, true);
+                    const uint32_t o = ks * 2;                        // 32 bytes >> 4
+                    mma_tf32(tmem, desc_k(aXl + o), desc_k(aYr + o), idesc_s, ks > 0);
+                    mma_tf32(tmem, desc_k(aXr + o), desc_k(aYl + o), idesc_s, true);
+                    mma_tf32(tmem, desc_k(aXr + o), desc_k(aYr + o), idesc_s, true);
                 }
                 tc_commit(&bars.y_empty[buf]);
                 tc_commit(&bars.s_full);
@@ -308,7 +311,7 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                 for (int kb = 0; kb < g.nkb; ++kb) issue_s(u++);           // pass A
             issue_s(u++);                                                   // pass B, first block
             uint32_t gc = 0;
-            const uint32_t half_off = (uint32_t)(g.n1 / 32) * blk_bytes;    // first block of the 2nd N half
+            const uint32_t half_off = ((uint32_t)(g.n1 / 32) * blk_bytes) >> 4;   // first block of the 2nd N half
             for (int kb = 0; kb < g.nkb; ++kb) {
                 if (kb + 1 < g.nkb) issue_s(u++);                           // next block's S while P*V runs
                 for (int c = 0; c < kPvChunks; ++c, ++gc) {
@@ -317,20 +320,20 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                     mbar_wait(&bars.w_ready[s], (gc / g.stages) & 1);
                     mbar_wait(&bars.p_full[slot], (gc >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t aWr = smem_u32(sWr(s)), aWl = smem_u32(sWl(s));
+                    const uint32_t aWr = mnmajor_lo(smem_u32(sWr(s)), blk_bytes), aWl = mnmajor_lo(smem_u32(sWl(s)), blk_bytes);
 #pragma unroll
                     for (int ks = 0; ks < kPvKC / 8; ++ks) {
                         const uint32_t ph = tmem + kPvPCol + slot * 32 + ks * 8, pl = ph + 16;
-                        const uint32_t wo = ks * 1024;
+                        const uint32_t wo = ks * 64;                     // 1024 bytes >> 4
                         const bool acc = (gc | ks) != 0;
-                        mma_tf32_ts(tmem + kPvOCol, pl, desc_mnmajor(aWr + wo, blk_bytes), idesc_o1, acc);
-                        mma_tf32_ts(tmem + kPvOCol, ph, desc_mnmajor(aWl + wo, blk_bytes), idesc_o1, true);
-                        mma_tf32_ts(tmem + kPvOCol, ph, desc_mnmajor(aWr + wo, blk_bytes), idesc_o1, true);
+                        mma_tf32_ts(tmem + kPvOCol, pl, desc_mn(aWr + wo), idesc_o1, acc);
+                        mma_tf32_ts(tmem + kPvOCol, ph, desc_mn(aWl + wo), idesc_o1, true);
+                        mma_tf32_ts(tmem + kPvOCol, ph, desc_mn(aWr + wo), idesc_o1, true);
                         if (g.n2 > 0) {
                             const uint32_t w2 = wo + half_off;
-                            mma_tf32_ts(tmem + kPvOCol + g.n1, pl, desc_mnmajor(aWr + w2, blk_bytes), idesc_o2, acc);
-                            mma_tf32_ts(tmem + kPvOCol + g.n1, ph, desc_mnmajor(aWl + w2, blk_bytes), idesc_o2, true);
-                            mma_tf32_ts(tmem + kPvOCol + g.n1, ph, desc_mnmajor(aWr + w2, blk_bytes), idesc_o2, true);
+                            mma_tf32_ts(tmem + kPvOCol + g.n1, pl, desc_mn(aWr + w2), idesc_o2, acc);
+                            mma_tf32_ts(tmem + kPvOCol + g.n1, ph, desc_mn(aWl + w2), idesc_o2, true);
+                            mma_tf32_ts(tmem + kPvOCol + g.n1, ph, desc_mn(aWr + w2), idesc_o2, true);
                         }
                     }
                     tc_commit(&bars.w_empty[s]);
@@ -596,8 +599,10 @@ __device__ __forceinline__ void nl_ds_body(const CUtensorMap& tmX, const CUtenso
             // ---- MMA issuer ----
             const uint32_t idesc_s = idesc_tf32(kPvM, kPvKB, false, false);
             const uint32_t idesc_o = idesc_tf32(kPvM, 32, false, true);
-            const uint32_t aXr = smem_u32(sXr), aXl = smem_u32(sXl), aYr = smem_u32(sYr), aYl = smem_u32(sYl);
-            const uint32_t aMr = smem_u32(sMr), aMl = smem_u32(sMl);
+            // descriptor low words (start address >> 4 | LBO): advancing an operand is a single add
+            const uint32_t aXr = kmajor_lo(smem_u32(sXr)), aXl = kmajor_lo(smem_u32(sXl));
+            const uint32_t aYr = kmajor_lo(smem_u32(sYr)), aYl = kmajor_lo(smem_u32(sYl));
+            const uint32_t aMr = mnmajor_lo(smem_u32(sMr), kTileBytes), aMl = mnmajor_lo(smem_u32(sMl), kTileBytes);
             mbar_wait(&bars.x_full, 0);
             mbar_wait(&bars.x_ready, 0);
             int gch = 0;
@@ -606,10 +611,10 @@ __device__ __forceinline__ void nl_ds_body(const CUtensorMap& tmX, const CUtenso
                 mbar_wait(&bars.y_ready, cb & 1);
                 tc_fence_after();
                 for (int ks = 0; ks < g.ksteps; ++ks) {
-                    const uint32_t o = ks * 32;
-                    mma_tf32(tmem, desc_kmajor(aXl + o), desc_kmajor(aYr + o), idesc_s, ks > 0);
-                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYl + o), idesc_s, true);
-                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYr + o), idesc_s, true);
+                    const uint32_t o = ks * 2;                        // 32 bytes >> 4
+                    mma_tf32(tmem, desc_k(aXl + o), desc_k(aYr + o), idesc_s, ks > 0);
+                    mma_tf32(tmem, desc_k(aXr + o), desc_k(aYl + o), idesc_s, true);
+                    mma_tf32(tmem, desc_k(aXr + o), desc_k(aYr + o), idesc_s, true);
                 }
                 tc_commit(&bars.y_empty);
                 for (int ch = 0; ch < g.nch; ++ch, ++gch) {
@@ -617,14 +622,14 @@ __device__ __forceinline__ void nl_ds_body(const CUtensorMap& tmX, const CUtenso
                     mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
                     mbar_wait(&bars.uw_ready[s], (gch >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t aUr = smem_u32(sU(s)), aUl = aUr + kTileBytes;
-                    const uint32_t aWr = smem_u32(sW(s)), aWl = aWr + kTileBytes;
+                    const uint32_t aUr = kmajor_lo(smem_u32(sU(s))), aUl = aUr + (kTileBytes >> 4);
+                    const uint32_t aWr = kmajor_lo(smem_u32(sW(s))), aWl = aWr + (kTileBytes >> 4);
                     const int nks = ch == g.nch - 1 ? g.last_ksteps : 4;
                     for (int ks = 0; ks < nks; ++ks) {
-                        const uint32_t o = ks * 32;
-                        mma_tf32(tmem + 128, desc_kmajor(aUl + o), desc_kmajor(aWr + o), idesc_s, (ch | ks) != 0);
-                        mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWl + o), idesc_s, true);
-                        mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWr + o), idesc_s, true);
+                        const uint32_t o = ks * 2;                        // 32 bytes >> 4
+                        mma_tf32(tmem + 128, desc_k(aUl + o), desc_k(aWr + o), idesc_s, (ch | ks) != 0);
+                        mma_tf32(tmem + 128, desc_k(aUr + o), desc_k(aWl + o), idesc_s, true);
+                        mma_tf32(tmem + 128, desc_k(aUr + o), desc_k(aWr + o), idesc_s, true);
                     }
                     tc_commit(&bars.uw_empty[s]);
                 }
@@ -635,10 +640,10 @@ __device__ __forceinline__ void nl_ds_body(const CUtensorMap& tmX, const CUtenso
                 tc_fence_after();
                 for (int ks = 0; ks < kPvKB / 8; ++ks) {
                     const uint32_t dh = tmem + ks * 8, dl = tmem + 128 + ks * 8;
-                    const uint32_t o = ks * 1024;
-                    mma_tf32_ts(tmem + kDsOCol, dl, desc_mnmajor(aMr + o, kTileBytes), idesc_o, (cb | ks) != 0);
-                    mma_tf32_ts(tmem + kDsOCol, dh, desc_mnmajor(aMl + o, kTileBytes), idesc_o, true);
-                    mma_tf32_ts(tmem + kDsOCol, dh, desc_mnmajor(aMr + o, kTileBytes), idesc_o, true);
+                    const uint32_t o = ks * 64;                       // 1024 bytes >> 4
+                    mma_tf32_ts(tmem + kDsOCol, dl, desc_mn(aMr + o), idesc_o, (cb | ks) != 0);
+                    mma_tf32_ts(tmem + kDsOCol, dh, desc_mn(aMl + o), idesc_o, true);
+                    mma_tf32_ts(tmem + kDsOCol, dh, desc_mn(aMr + o), idesc_o, true);
                 }
                 tc_commit(&bars.ymn_empty);
             }
@@ -855,42 +860,43 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
                 mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
                 mbar_wait(&bars.uw_ready[s], (gch >> 1) & 1);
                 tc_fence_after();
-                const uint32_t aUr = smem_u32(sU(s)), aUl = aUr + kTileBytes;
-                const uint32_t aWr = smem_u32(sW(s)), aWl = aWr + 2 * kTileBytes;
+                // descriptor low words (start address >> 4 | LBO): advancing an operand is a single add
+                const uint32_t aUr = kmajor_lo(smem_u32(sU(s))), aUl = aUr + (kTileBytes >> 4);
+                const uint32_t aWr = kmajor_lo(smem_u32(sW(s))), aWl = aWr + (2 * kTileBytes >> 4);
                 const int nks = gch == nch - 1 ? g.last_ksteps : 4;
                 for (int ks = 0; ks < nks; ++ks) {
-                    const uint32_t o = ks * 32;
-                    mma_tf32(tmem + 128, desc_kmajor(aUl + o), desc_kmajor(aWr + o), idesc_p, (gch | ks) != 0);
-                    mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWl + o), idesc_p, true);
-                    mma_tf32(tmem + 128, desc_kmajor(aUr + o), desc_kmajor(aWr + o), idesc_p, true);
+                    const uint32_t o = ks * 2;                        // 32 bytes >> 4
+                    mma_tf32(tmem + 128, desc_k(aUl + o), desc_k(aWr + o), idesc_p, (gch | ks) != 0);
+                    mma_tf32(tmem + 128, desc_k(aUr + o), desc_k(aWl + o), idesc_p, true);
+                    mma_tf32(tmem + 128, desc_k(aUr + o), desc_k(aWr + o), idesc_p, true);
                 }
                 tc_commit(&bars.uw_empty[s]);
             }
             tc_commit(&bars.dp_done);
             mbar_wait(&bars.x_full, 0);
             mbar_wait(&bars.x_ready, 0);
-            const uint32_t aXr = smem_u32(sXr), aXl = smem_u32(sXl);
+            const uint32_t aXr = kmajor_lo(smem_u32(sXr)), aXl = kmajor_lo(smem_u32(sXl));
             for (int cb = 0; cb < 2; ++cb) {
                 mbar_wait(&bars.y_full[cb], 0);
                 mbar_wait(&bars.y_ready[cb], 0);
                 tc_fence_after();
-                const uint32_t aYr = smem_u32(sYr(cb)), aYl = smem_u32(sYl(cb));
-                const uint32_t aMr = smem_u32(sMr(cb)), aMl = smem_u32(sMl(cb));
+                const uint32_t aYr = kmajor_lo(smem_u32(sYr(cb))), aYl = kmajor_lo(smem_u32(sYl(cb)));
+                const uint32_t aMr = mnmajor_lo(smem_u32(sMr(cb)), kTileBytes), aMl = mnmajor_lo(smem_u32(sMl(cb)), kTileBytes);
                 for (int ks = 0; ks < g.ksteps; ++ks) {
-                    const uint32_t o = ks * 32;
-                    mma_tf32(tmem, desc_kmajor(aXl + o), desc_kmajor(aYr + o), idesc_s, ks > 0);
-                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYl + o), idesc_s, true);
-                    mma_tf32(tmem, desc_kmajor(aXr + o), desc_kmajor(aYr + o), idesc_s, true);
+                    const uint32_t o = ks * 2;                        // 32 bytes >> 4
+                    mma_tf32(tmem, desc_k(aXl + o), desc_k(aYr + o), idesc_s, ks > 0);
+                    mma_tf32(tmem, desc_k(aXr + o), desc_k(aYl + o), idesc_s, true);
+                    mma_tf32(tmem, desc_k(aXr + o), desc_k(aYr + o), idesc_s, true);
                 }
                 tc_commit(&bars.s_full);
                 mbar_wait(&bars.ds_full, cb & 1);
                 tc_fence_after();
                 for (int ks = 0; ks < kPvKB / 8; ++ks) {
                     const uint32_t dh = tmem + ks * 8, dl = tmem + 128 + cb * 128 + ks * 8;
-                    const uint32_t o = ks * 1024;
-                    mma_tf32_ts(tmem + kD2OCol, dl, desc_mnmajor(aMr + o, kTileBytes), idesc_o, (cb | ks) != 0);
-                    mma_tf32_ts(tmem + kD2OCol, dh, desc_mnmajor(aMl + o, kTileBytes), idesc_o, true);
-                    mma_tf32_ts(tmem + kD2OCol, dh, desc_mnmajor(aMr + o, kTileBytes), idesc_o, true);
+                    const uint32_t o = ks * 64;                       // 1024 bytes >> 4
+                    mma_tf32_ts(tmem + kD2OCol, dl, desc_mn(aMr + o), idesc_o, (cb | ks) != 0);
+                    mma_tf32_ts(tmem + kD2OCol, dh, desc_mn(aMl + o), idesc_o, true);
+                    mma_tf32_ts(tmem + kD2OCol, dh, desc_mn(aMr + o), idesc_o, true);
                 }
             }
             tc_commit(&bars.o_full);

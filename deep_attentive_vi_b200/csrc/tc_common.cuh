@@ -171,6 +171,20 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t block_
     return smem_desc_sw(saddr, block_bytes, 512, kLayoutSw128Base32);
 }
 
+// The same two descriptors as (low word, constant high word): inside an MMA issue loop the operand moves by a
+// multiple of 16 bytes, so the next descriptor is ONE 32-bit add of (bytes >> 4) to the low word instead of the
+// add / shift / mask / or chain on the uniform datapath (6-13 instead of 16-17 instructions between MMAs; worth
+// 1-2 % in the kernels, which are bound by the softmax -> P -> MMA dependency chain, not by issue).
+// Shared-memory addresses stay below 2^18, so the 14-bit address field never carries into the LBO field.
+constexpr uint32_t kDescHiKmajor = (1024u >> 4) | (1u << 14) | (kLayoutSw128 << 29);
+constexpr uint32_t kDescHiMnmajor = (512u >> 4) | (1u << 14) | (kLayoutSw128Base32 << 29);
+__device__ __forceinline__ uint32_t kmajor_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ uint32_t mnmajor_lo(uint32_t saddr, uint32_t block_bytes) {
+    return ((saddr >> 4) & 0x3fffu) | (((block_bytes >> 4) & 0x3fffu) << 16);
+}
+__device__ __forceinline__ uint64_t desc_k(uint32_t lo) { return ((uint64_t)kDescHiKmajor << 32) | lo; }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t lo) { return ((uint64_t)kDescHiMnmajor << 32) | lo; }
+
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (M=128 lanes x 8 columns per k-step) is read from TMEM
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             bool accumulate) {
