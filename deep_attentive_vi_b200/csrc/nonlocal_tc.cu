@@ -35,6 +35,21 @@ namespace davi {
 
 using namespace tc;
 
+// Optional phase trace for profiling sessions: tools/nl_trace.py builds a SECOND library with -DDAVI_NL_TRACE and
+// reads the stamps; the product build compiles none of it (NL_STAMP expands to nothing).  One designated thread
+// per stamp index writes clock64() of its SM; only CTA (0, 0, z) of a grid stamps, row z of the buffer.
+#ifdef DAVI_NL_TRACE
+__device__ long long g_nl_trace[3][32];
+#define NL_STAMP(i)                                          \
+    do {                                                     \
+        if (blockIdx.x == 0 && blockIdx.y == 0) g_nl_trace[blockIdx.z][i] = clock64(); \
+    } while (0)
+#else
+#define NL_STAMP(i) \
+    do {            \
+    } while (0)
+#endif
+
 constexpr int kPvM = 128;                   // rows per CTA
 constexpr int kPvKB = 128;                  // columns per S block
 constexpr int kPvKC = 16;                   // columns per P chunk
@@ -98,6 +113,7 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, r0 = blockIdx.x * kPvM;
     const int nchunks = g.nkb * kPvChunks;
+    if (tid == 0) NL_STAMP(0);                             // entry
     const int nuse = (MODE == 0 ? 2 : 1) * g.nkb;          // S blocks issued (pass A + pass B)
 
     uint8_t* sXr = smem;
@@ -148,6 +164,7 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars.tmem_base;
+    if (tid == 0) NL_STAMP(1);                             // barriers, TMEM, descriptors ready
 
     if (warp < 4) {
         // =====================================================================
@@ -178,6 +195,7 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                 for (int j = 0; j < kPvKB; ++j) m = fmaxf(m, t[j] * sc);
             }
         }
+        if (r == 0) NL_STAMP(6);                           // softmax: pass A (row max) done
         uint32_t gc = 0;
         for (int kb = 0; kb < g.nkb; ++kb) {               // pass B: P chunks -> TMEM
             load_s();
@@ -200,11 +218,14 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars.p_full[slot]);
+                if (r == 0 && gc == 0) NL_STAMP(7);        // softmax: first P chunk handed over
             }
         }
+        if (r == 0) NL_STAMP(8);                           // softmax: last P chunk handed over
 
         // ---- epilogue, part 1: accumulator rows -> shared memory (the operand buffers are free) ----
         mbar_wait(&bars.o_full, 0);
+        if (r == 0) NL_STAMP(9);                           // accumulator complete
         tc_fence_after();
         const float rs = MODE == 0 ? 1.f / l : 1.f;
         if (MODE == 0) a.lse[(int64_t)b * g.N + r0 + r] = (m + log2f(l)) * kLn2;
@@ -306,10 +327,12 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
             };
             mbar_wait(&bars.x_full, 0);
             mbar_wait(&bars.x_ready, 0);
+            NL_STAMP(2);                                                    // MMA: X tile + lo image ready
             int u = 0;
             if (MODE == 0)
                 for (int kb = 0; kb < g.nkb; ++kb) issue_s(u++);           // pass A
             issue_s(u++);                                                   // pass B, first block
+            NL_STAMP(3);                                                    // MMA: pass A + first pass-B S issued
             uint32_t gc = 0;
             const uint32_t half_off = ((uint32_t)(g.n1 / 32) * blk_bytes) >> 4;   // first block of the 2nd N half
             for (int kb = 0; kb < g.nkb; ++kb) {
@@ -320,6 +343,7 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                     mbar_wait(&bars.w_ready[s], (gc / g.stages) & 1);
                     mbar_wait(&bars.p_full[slot], (gc >> 1) & 1);
                     tc_fence_after();
+                    if (gc == 0) NL_STAMP(4);                               // MMA: first P / W chunk available
                     const uint32_t aWr = mnmajor_lo(smem_u32(sWr(s)), blk_bytes), aWl = mnmajor_lo(smem_u32(sWl(s)), blk_bytes);
 #pragma unroll
                     for (int ks = 0; ks < kPvKC / 8; ++ks) {
@@ -341,12 +365,14 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
                 }
             }
             tc_commit(&bars.o_full);
+            NL_STAMP(5);                                                    // MMA: everything issued
             tc_fence_before();
         }
         __syncwarp();
     }
 
     __syncthreads();
+    if (tid == 0) NL_STAMP(10);                            // tile staged in shared memory
     if (warp == 10) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
@@ -390,6 +416,7 @@ __device__ __forceinline__ void nl_pv_body(const CUtensorMap& tmX, const CUtenso
             }
         }
     }
+    if (tid == 0) NL_STAMP(11);                            // this thread's share of the tile stored
 }
 
 template <int MODE>
@@ -689,6 +716,7 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, r0 = blockIdx.x * kPvM;
+    if (tid == 0) NL_STAMP(0);                             // entry
 
     auto sU = [&](int s) { return smem + s * kD2StageBytes; };                       // raw, +16K lo
     auto sW = [&](int s) { return smem + s * kD2StageBytes + 2 * kTileBytes; };      // raw 32K, +32K lo
@@ -739,6 +767,7 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
         float dsc = 0.f;
         for (int cb = 0; cb < 2; ++cb) {
             mbar_wait(&bars.s_full, cb & 1);          // S(cb) done; the dp MMAs were issued (and finished) before it
+            if (tid == 0) NL_STAMP(10 + 2 * cb);      // dS warps: S(cb) (and, for cb = 0, all of dp) complete
             tc_fence_after();
             const uint32_t dpc = 128 + cb * 128;
 #pragma unroll 1
@@ -770,6 +799,7 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars.ds_full);
+            if (tid == 0) NL_STAMP(11 + 2 * cb);      // dS warps: dS(cb) handed over
         }
         if (MODE == 0 && a.dscale) {
             dsc = group_sum<32>(dsc);
@@ -790,6 +820,7 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
         ds_phase(0);
         const float gs = __ldg(a.gamma) * scale;
         mbar_wait(&bars.o_full, 0);
+        if (tid == 0) NL_STAMP(14);                   // accumulator complete
         tc_fence_after();
         float o[32];
         tmem_ld32(trow + kD2OCol, o);
@@ -860,6 +891,7 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
                 mbar_wait(&bars.uw_full[s], (gch >> 1) & 1);
                 mbar_wait(&bars.uw_ready[s], (gch >> 1) & 1);
                 tc_fence_after();
+                if (gch == 0) NL_STAMP(2);                      // MMA: first U / W chunk + lo images ready
                 // descriptor low words (start address >> 4 | LBO): advancing an operand is a single add
                 const uint32_t aUr = kmajor_lo(smem_u32(sU(s))), aUl = aUr + (kTileBytes >> 4);
                 const uint32_t aWr = kmajor_lo(smem_u32(sW(s))), aWl = aWr + (2 * kTileBytes >> 4);
@@ -873,6 +905,7 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
                 tc_commit(&bars.uw_empty[s]);
             }
             tc_commit(&bars.dp_done);
+            NL_STAMP(3);                                        // MMA: dp issued for all chunks
             mbar_wait(&bars.x_full, 0);
             mbar_wait(&bars.x_ready, 0);
             const uint32_t aXr = kmajor_lo(smem_u32(sXr)), aXl = kmajor_lo(smem_u32(sXl));
@@ -889,7 +922,9 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
                     mma_tf32(tmem, desc_k(aXr + o), desc_k(aYr + o), idesc_s, true);
                 }
                 tc_commit(&bars.s_full);
+                NL_STAMP(4 + 2 * cb);                           // MMA: S(cb) issued
                 mbar_wait(&bars.ds_full, cb & 1);
+                NL_STAMP(5 + 2 * cb);                           // MMA: dS(cb) written by the 8 warps
                 tc_fence_after();
                 for (int ks = 0; ks < kPvKB / 8; ++ks) {
                     const uint32_t dh = tmem + ks * 8, dl = tmem + 128 + cb * 128 + ks * 8;
@@ -900,6 +935,7 @@ __device__ __forceinline__ void nl_ds256_body(const CUtensorMap& tmX, const CUte
                 }
             }
             tc_commit(&bars.o_full);
+            NL_STAMP(8);                                        // MMA: everything issued
             tc_fence_before();
         }
         __syncwarp();
@@ -1174,3 +1210,10 @@ int nonlocal_bwd_tc_launch(const float* Q, const float* K, const float* V, const
 }
 
 }  // namespace davi
+
+#ifdef DAVI_NL_TRACE
+// trace build only (tools/nl_trace.py): copies the [3][32] clock64 stamps of the last launches to the host
+extern "C" int davi_nl_trace_read(long long* host_3x32) {
+    return cudaMemcpyFromSymbol(host_3x32, davi::g_nl_trace, sizeof(long long) * 96) == cudaSuccess ? 0 : -1;
+}
+#endif
