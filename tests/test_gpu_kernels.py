@@ -304,7 +304,7 @@ def test_split_tf32_parts_are_exact(cuda):
                                                       (40, 16, 128, 128, 3, 1, 1)])
 def test_conv_3xtf32_is_fp32_grade(cuda, B, HW, ci, co, k, stride, pad):
     """The default conv precision (split operands, one TF32 cuDNN call over a tripled contraction axis)
-    against an fp64 convolution: output and all three gradients within 2e-5 of the tensor's max-abs.
+    against an fp64 convolution: output and all three gradients within 3e-5 of the tensor's max-abs.
     Measured 1e-6 (contraction length 81) .. 1.1e-5 (length 3 456), growing with the contraction length:
     the products carry ~2^-21 and the tensor core's fp32 accumulator truncates instead of rounding;
     cuDNN's CUDA-core fp32 sits at ~1e-6, plain TF32 at ~5e-4."""
@@ -322,9 +322,9 @@ def test_conv_3xtf32_is_fp32_grade(cuda, B, HW, ci, co, k, stride, pad):
     yd = torch.nn.functional.conv2d(xd, wd, bd, stride=stride, padding=pad)
     gd = torch.autograd.grad(yd, (xd, wd, bd), go.double())
     err = lambda a, c: ((a.double() - c).abs().max() / c.abs().max()).item()
-    assert err(y, yd) < 2e-5
+    assert err(y, yd) < 3e-5
     for a, c, name in zip(g, gd, "x w b".split()):
-        assert err(a, c) < 2e-5, (name, err(a, c))
+        assert err(a, c) < 3e-5, (name, err(a, c))
     assert g[0].is_contiguous(memory_format=torch.channels_last) and g[1].is_contiguous(memory_format=torch.channels_last)
 
 
