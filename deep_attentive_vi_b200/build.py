@@ -34,8 +34,8 @@ def _digest():
     for p in _sources() + sorted(
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
     ) + [os.path.join(ROOT, "include", "davi.h")]:
-        with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
+        with open(p, "rb") as f:        # repo-relative names: the snapshot on the GPU box lives under another root
+            h.update(os.path.relpath(p, ROOT).encode() + b"\0" + f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
