@@ -22,6 +22,8 @@ _lp = ctypes.POINTER(ctypes.c_int64)
 SIGNATURES = {
     "davi_version": (_i, []),
     "davi_last_error": (_i, [ctypes.c_char_p, _z]),
+    "davi_set_option": (_i, [_i, _i]),
+    "davi_get_option": (_i, [_i]),
     "davi_dw_attn_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _l, _l, _f, _s]),
     "davi_dw_attn_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _l, _l, _f, _s]),
     "davi_dw_attn_slots_fwd": (_i, [_f, _pp, _pp, _lp, _lp, _f, _f, _i, _i, _i, _i, _i, _l, _l, _f, _s]),
@@ -51,6 +53,10 @@ SIGNATURES = {
     "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
     "davi_adamax_step_dev": (_i, [_f, _f, _f, _f, _l, _f, _r, _r, _r, _r, _s]),
 }
+
+
+# davi_set_option switches (include/davi.h)
+OPT_DW_IMPL, OPT_NONLOCAL_IMPL, OPT_NL_DS, OPT_NL_BWD = 0, 1, 2, 3
 
 
 class DaviError(RuntimeError):
@@ -110,6 +116,10 @@ def call(name, *args):
     global _launches
     check(getattr(load(), name)(*args), name)
     _launches += KERNELS_PER_CALL.get(name, 1)
+
+
+def set_option(option, value):
+    check(load().davi_set_option(option, value), "davi_set_option")
 
 
 def ptr_table(ptrs):

@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "davi_common.cuh"
 
 namespace davi {
@@ -26,7 +28,25 @@ int check_launch(const char* what) {
     return DAVI_OK;
 }
 
+// process-wide implementation switches (davi_set_option): relaxed atomics, read on every call
+static std::atomic<int> g_options[DAVI_OPT_COUNT_];
+
+int get_option(int option) {
+    return (option >= 0 && option < DAVI_OPT_COUNT_) ? g_options[option].load(std::memory_order_relaxed) : 0;
+}
+
 }  // namespace davi
+
+extern "C" int davi_set_option(int option, int value) {
+    if (option < 0 || option >= DAVI_OPT_COUNT_) {
+        davi::set_error("davi_set_option: unknown option %d", option);
+        return DAVI_EINVAL;
+    }
+    davi::g_options[option].store(value, std::memory_order_relaxed);
+    return DAVI_OK;
+}
+
+extern "C" int davi_get_option(int option) { return davi::get_option(option); }
 
 extern "C" int davi_version(void) { return DAVI_VERSION; }
 

@@ -13,6 +13,8 @@ namespace davi {
 void set_error(const char* fmt, ...);
 // cudaPeekAtLastError() after a launch; records text, returns DAVI_OK / DAVI_ECUDA
 int check_launch(const char* what);
+// current value of a davi_set_option() switch (0 = default)
+int get_option(int option);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool mult4(int64_t v) { return (v & 3) == 0; }

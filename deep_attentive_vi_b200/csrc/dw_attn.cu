@@ -609,15 +609,8 @@ static void launch_bwd(const SlotPtrs& sp, const SlotGradPtrs& gp, const float* 
         }                                                          \
     } while (0)
 
-// DAVI_DW_IMPL=v1 selects the register-streaming kernels (read once per process)
-static bool dw_v2_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("DAVI_DW_IMPL");
-        v = (e && strcmp(e, "v1") == 0) ? 0 : 1;
-    }
-    return v == 1;
-}
+// davi_set_option(DAVI_OPT_DW_IMPL, 1) selects the register-streaming kernels for every shape
+static bool dw_v2_enabled() { return get_option(DAVI_OPT_DW_IMPL) != 1; }
 
 static int dw_fwd_impl(const char* fn, const SlotPtrs& sp, const float* q, float* out, float* attn,
                        int B, int n, int P, int d, int C, DwGeom g, cudaStream_t st) {

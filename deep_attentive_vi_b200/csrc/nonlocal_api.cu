@@ -23,15 +23,8 @@ int nonlocal_bwd_tc_launch(const float*, const float*, const float*, const float
                            int64_t, const float*, const float*, float*, cudaStream_t);
 #endif
 
-// DAVI_NONLOCAL_IMPL=simt forces the exact-fp32 kernels (read once per process).
-static bool force_simt() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("DAVI_NONLOCAL_IMPL");
-        v = (e && strcmp(e, "simt") == 0) ? 1 : 0;
-    }
-    return v == 1;
-}
+// davi_set_option(DAVI_OPT_NONLOCAL_IMPL, 1) forces the exact-fp32 CUDA-core kernels
+static bool force_simt() { return get_option(DAVI_OPT_NONLOCAL_IMPL) == 1; }
 }  // namespace davi
 
 using namespace davi;

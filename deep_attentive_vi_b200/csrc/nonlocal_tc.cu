@@ -1128,7 +1128,7 @@ static DsGeom ds_geom(int N, int d, int C) {
     g.nch = (C + 31) / 32;
     g.ksteps = (d + 7) / 8;
     g.last_ksteps = (C - 32 * (g.nch - 1) + 7) / 8;
-    static const bool no_v2 = [] { const char* e = getenv("DAVI_NL_DS"); return e && strcmp(e, "v1") == 0; }();
+    const bool no_v2 = get_option(DAVI_OPT_NL_DS) == 1;
     g.v2 = (N == 256 && !no_v2) ? 1 : 0;
     return g;
 }
@@ -1163,7 +1163,7 @@ int nonlocal_bwd_tc_launch(const float* Q, const float* K, const float* V, const
     int rc = check_launch(fn);
     if (rc) return rc;
 
-    static const bool split = [] { const char* e = getenv("DAVI_NL_BWD"); return e && strcmp(e, "split") == 0; }();
+    const bool split = get_option(DAVI_OPT_NL_BWD) == 1;
     if (split) {                                       // three launches (A/B switch for profiling)
         rc = nonlocal_dv_tc_launch(Q, K, lse, dy, dV, B, N, d, C, q_s, k_s, dy_s, v_s, scale, gamma, st);
         if (rc) return rc;

@@ -736,8 +736,7 @@ class _ConvBias3x(torch.autograd.Function):
 def conv2d_bias(x, w, b, stride=1, padding=0):
     """F.conv2d(x, w, b) on NCHW views of channels_last tensors, with the fast bias gradient, in the
     precision selected by set_conv_precision()."""
-    if not x.is_cuda:
-        return torch.nn.functional.conv2d(x, w, b, stride=stride, padding=padding)
+    _require_cuda(x, w, b)
     if _conv_precision == "3xtf32":
         if not torch.backends.cudnn.allow_tf32:
             raise RuntimeError("conv precision '3xtf32' needs torch.backends.cudnn.allow_tf32 = True "

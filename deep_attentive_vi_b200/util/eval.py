@@ -66,19 +66,43 @@ class GraphedChunks:
         return out.clone()
 
 
+_rank_streams = set()
+
+
+def decorrelate_rank_rng(device, rank, world):
+    """Sample sharding is only an estimator with K samples if every rank draws DIFFERENT ones; ranks
+    usually share one seed (identical weights).  Offsets this rank's CUDA generator by a rank-dependent
+    amount once per (device, rank): same seed, disjoint Philox subsequences."""
+    key = (str(device), rank, world)
+    if world <= 1 or key in _rank_streams:
+        return
+    _rank_streams.add(key)
+    gen = torch.cuda.default_generators[torch.device(device).index or 0] if torch.device(device).type == "cuda" \
+        else torch.default_generator
+    if torch.device(device).type == "cuda":
+        gen.set_offset(gen.get_offset() + (rank + 1) * (1 << 40))          # multiples of 4 (Philox requirement)
+    else:
+        gen.manual_seed(gen.initial_seed() + 7919 * (rank + 1))
+
+
 @torch.no_grad()
 def importance_log_likelihood(model, x, num_samples, max_chunk=25, world=1, rank=0, group=None, chunks=None):
     """log p_hat(x) [B] with K = num_samples importance samples, this rank
     computing its shard in chunks of at most `max_chunk` samples.  `chunks`: a GraphedChunks
-    instance to replay CUDA graphs instead of launching every chunk eagerly."""
+    instance to replay CUDA graphs instead of launching every chunk eagerly.  Ranks draw from
+    decorrelated generator streams; a rank whose shard is empty (K < world) contributes -inf."""
     lo, hi = shard_samples(num_samples, world, rank)
+    decorrelate_rank_rng(x.device, rank, world)
     parts = []
     k = lo
     while k < hi:
         n = min(max_chunk, hi - k)
         parts.append(chunks(x, n) if chunks is not None else model.infer_worker_body(x, n))
         k += n
-    local = torch.logsumexp(torch.stack(parts, 0), dim=0)            # [B]
+    if parts:
+        local = torch.logsumexp(torch.stack(parts, 0), dim=0)        # [B]
+    else:
+        local = torch.full((x.shape[0],), float("-inf"), device=x.device, dtype=torch.float32)
     if world > 1:
         gathered = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(gathered, local, group=group)

@@ -14,6 +14,7 @@ flat fp32 arrays (476 MB each for the CIFAR-10 model), so the all-reduce is one
 NCCL call on one buffer and the optimizer + l2-regulariser gradient is one fused
 kernel pass per regulariser class (davi_adamax_step).
 """
+import copy
 import math
 
 import torch
@@ -24,24 +25,47 @@ from ..util.hparams import HParams
 
 
 def get_default_train_hparams():
-    """tr.py:207-233."""
+    """tr.py:207-233.  lr_decay_epochs / lr_steps_per_epoch carry the reference's defaults (1000 / 1563);
+    like keras_train (tr.py:139-140) the Trainer overwrites them with epochs - lr_warmup_epochs and
+    train_size / (num_gpus * batch_size) when it is told the training-set size."""
     return HParams(num_gpus=1, batch_size=256, epochs=400, learning_rate=1e-2,
-                   learning_rate_schedule="cosine_warmup", lr_warmup_epochs=5, lr_min_learning_rate=1e-4,
+                   learning_rate_schedule="cosine_warmup", lr_decay_epochs=1000, lr_steps_per_epoch=1563,
+                   lr_warmup_epochs=5, lr_min_learning_rate=1e-4,
                    lr_first_decay_epochs=100, lr_t_mul=2.0, lr_m_mul=1.0, optimizer="adamax",
                    keras_lr_beta_1=0.9, keras_lr_beta_2=0.999, keras_lr_epsilon=1e-3,
                    kl_warmup_epochs=16, kl_warmup_smooth_start=0.1)
 
 
-def l2_coefficient(name, lambda_reg=1.5e-4, keras_default=0.01):
-    """Regulariser strength of a parameter by name:
-    conv v / g / bias, batch-norm gamma/beta and the nonlocal logit scale are
-    built with REGULARIZER['l2'](l=lambda_reg); everything that received the bare
-    string 'l2' (LayerNorm weights, the gamma scalars, the layer-0 constant) uses
-    Keras' default 0.01."""
-    leaf = name.rsplit(".", 1)[-1]
-    if leaf in ("v", "log_g", "bias", "scale") or ".bn." in name:
-        return lambda_reg
-    return keras_default
+def regulariser_coefficients(model):
+    """l2 strength of every trainable parameter, read off the model's OWN regulariser (the modules'
+    reg_loss() methods: one source of truth, per-layer lambda_reg and disabled regularisers included).
+    reg_loss is a quadratic form sum_i c_i p_i^2, so its gradient at p = 1 is 2 c_i.  Returns
+    {parameter: c}; a parameter the regulariser does not touch gets 0."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    saved = [p.detach().clone() for p in params]
+    try:
+        with torch.no_grad():
+            for p in params:
+                p.fill_(1.0)
+        reg = model.reg_loss()
+        grads = (torch.autograd.grad(reg, params, allow_unused=True) if torch.is_tensor(reg) and reg.requires_grad
+                 else [None] * len(params))
+    finally:
+        with torch.no_grad():
+            for p, v in zip(params, saved):
+                p.copy_(v)
+    out = {}
+    for p, g in zip(params, grads):
+        if g is None:
+            out[p] = 0.0
+            continue
+        c = 0.5 * g.reshape(-1)
+        lo, hi = float(c.min()), float(c.max())
+        if hi - lo > 1e-6 * max(abs(hi), 1e-30):
+            raise ValueError("regulariser strength varies inside one parameter tensor; the fused optimizer "
+                             "applies one coefficient per tensor")
+        out[p] = float(c[0])
+    return out
 
 
 def kl_beta(epoch, warmup_epochs=16, smooth_start=0.1):
@@ -52,14 +76,19 @@ def kl_beta(epoch, warmup_epochs=16, smooth_start=0.1):
 
 
 def cosine_warmup_lr(step, steps_per_epoch, lr, min_lr, warmup_epochs, decay_epochs):
-    """CosineWarmup (util/learning_rate_schedule.py:189-277): linear warm-up per
-    step from min_lr to lr, then cosine decay per epoch down to min_lr."""
+    """CosineWarmup.__call__ (util/learning_rate_schedule.py:229-268) at the callback's 1-based
+    global_step (LearningRateScheduler increments it BEFORE the call, :60-68): linear per-step warm-up
+    min_lr + step / warmup_steps * (lr - min_lr) while step <= warmup_steps, then a per-epoch cosine of
+    local_epoch / decay_epochs; past decay_epochs the reference keeps its last value, which is min_lr."""
     warm = warmup_epochs * steps_per_epoch
-    if step < warm:
-        return min_lr + (lr - min_lr) * step / max(1, warm)
-    epoch = (step - warm) // steps_per_epoch
-    frac = min(1.0, epoch / max(1, decay_epochs))
-    return min_lr + 0.5 * (lr - min_lr) * (1.0 + math.cos(math.pi * frac))
+    if step <= warm:
+        return min_lr + float(step / warm) * (lr - min_lr)
+    local_epoch = step // steps_per_epoch - warmup_epochs
+    if local_epoch > decay_epochs:
+        return min_lr
+    alpha = min_lr / lr
+    cosine = 0.5 * (1.0 + math.cos(math.pi * (local_epoch / decay_epochs)))
+    return lr * ((1.0 - alpha) * cosine + alpha)
 
 
 class FlatState:
@@ -71,9 +100,10 @@ class FlatState:
 
     def __init__(self, model, device):
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        coef = regulariser_coefficients(model)
         groups = {}
         for n, p in named:
-            groups.setdefault(l2_coefficient(n), []).append((n, p))
+            groups.setdefault(round(coef[p], 12), []).append((n, p))
         total = sum(p.numel() for _, p in named)
         pad = lambda k: (k + 63) // 64 * 64   # every tensor starts 256-byte aligned (cuDNN, float4 loads)
         size = sum(sum(pad(p.numel()) for _, p in g) for g in groups.values())
@@ -208,16 +238,23 @@ class Trainer:
     step then cost one host call.  Everything that changes between steps lives in
     device memory (input batch, KL weight beta, Adamax step size)."""
 
-    def __init__(self, model, hparams=None, device="cuda", world_size=1, rank=0, steps_per_epoch=1250,
+    def __init__(self, model, hparams=None, device="cuda", world_size=1, rank=0, train_size=None, batch_size=None,
                  use_graph=False, graph_warmup=3, use_schedule=True):
+        """train_size / batch_size (per GPU): when given, the schedule lengths are derived like keras_train does
+        (tr.py:139-140): lr_steps_per_epoch = int(train_size / (num_gpus * batch_size)), lr_decay_epochs =
+        epochs - lr_warmup_epochs; otherwise the hparams' own values are used."""
         self.model = model
         self.use_schedule = use_schedule
-        self.hp = hparams or get_default_train_hparams()
+        self.hp = copy.deepcopy(hparams) if hparams is not None else get_default_train_hparams()
         self.device = torch.device(device)
         self.world, self.rank = world_size, rank
         self.state = FlatState(model, self.device)
         self.step_count = 0
-        self.steps_per_epoch = steps_per_epoch
+        if train_size is not None:
+            bs = batch_size if batch_size is not None else self.hp.batch_size
+            self.hp["lr_steps_per_epoch"] = int(train_size / (world_size * bs))
+            self.hp["lr_decay_epochs"] = self.hp.epochs - self.hp.lr_warmup_epochs
+        self.steps_per_epoch = self.hp.lr_steps_per_epoch
         self.beta = 1.0
         self.lr = self.hp.learning_rate
         if use_schedule:      # epoch 0 of the reference run: lr = lr_min (warm-up), beta = 0.1 (KL warm-up)
@@ -245,6 +282,8 @@ class Trainer:
     def forward_backward(self, x, eps=None, noise=None):
         st = self.state
         st.G.zero_()                                                 # parameters that get no gradient this step
+        if st.wn_rows:
+            st.dW.zero_()                                            # ... and conv kernels likewise (no stale dW)
         st.clear_grads()
         stream = torch.cuda.current_stream().cuda_stream
         if st.wn_rows:                                               # all conv kernels: v, log_g -> W
@@ -272,10 +311,10 @@ class Trainer:
         (per step, like the reference's Keras callback, util/learning_rate_schedule.py:55-79)
         and push a changed value (fill_ carries it in the launch arguments: no pinned-buffer race)."""
         hp = self.hp
+        self.step_count += 1            # the reference's callback counts the step before asking the schedule
         if self.use_schedule and hp.learning_rate_schedule == "cosine_warmup":
             self.lr = cosine_warmup_lr(self.step_count, self.steps_per_epoch, hp.learning_rate,
-                                       hp.lr_min_learning_rate, hp.lr_warmup_epochs, hp.lr_first_decay_epochs)
-        self.step_count += 1
+                                       hp.lr_min_learning_rate, hp.lr_warmup_epochs, hp.lr_decay_epochs)
         if float(self.lr) != self._lr_pushed:
             self._lr_pushed = float(self.lr)
             self.lr_dev.fill_(self._lr_pushed)
@@ -331,4 +370,5 @@ class Trainer:
         self._static["x"].copy_(x, non_blocking=True)
         self._graph.replay()
         _lib.add_launches(self.graph_launches)
-        return self._static["nll"], self._static["kl"]
+        # fresh tensors, like the eager path: the next replay overwrites the capture's static outputs
+        return self._static["nll"].clone(), self._static["kl"].clone()

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DAVI_VERSION 104          /* major*100 + minor */
+#define DAVI_VERSION 200          /* major*100 + minor */
 #define DAVI_MAX_SLOTS 32         /* max stacked layers n of the depth-wise attention */
 
 #define DAVI_OK 0
@@ -49,6 +49,17 @@ typedef void* davi_stream_t;      /* cudaStream_t */
 int davi_version(void);
 /* copies the calling thread's last error text (NUL terminated) into buf */
 int davi_last_error(char* buf, size_t buf_bytes);
+
+/* Implementation switches for tests and profiling (A/B of kernel variants; results are identical
+ * within the stated tolerances).  Process-wide relaxed atomics read on every call: safe to set
+ * from any thread, never read from the environment.  value 0 = default. */
+#define DAVI_OPT_DW_IMPL 0        /* 1: register-streaming depth-wise kernels for every shape   */
+#define DAVI_OPT_NONLOCAL_IMPL 1  /* 1: exact-fp32 CUDA-core nonlocal kernels instead of tcgen05 */
+#define DAVI_OPT_NL_DS 2          /* 1: per-block dQ/dK variant also for N = 256                */
+#define DAVI_OPT_NL_BWD 3         /* 1: nonlocal gradient as three launches instead of one      */
+#define DAVI_OPT_COUNT_ 8
+int davi_set_option(int option, int value);
+int davi_get_option(int option);
 
 /* ------------------------------------------------------------------------
  * R1  Depth-wise attention, stacked tensors.

@@ -44,13 +44,25 @@ def test_ctypes_table_matches_header(libdavi):
 
 
 def test_version_and_error_text(libdavi):
-    assert libdavi.davi_version() == 104
+    assert libdavi.davi_version() == 200
     rc = libdavi.davi_dw_attn_fwd(None, None, None, None, None, 1, 1, 1, 4, 4,
                                   4, 4, 4, 4, 4, 4, 4, 4, None, None)
     assert rc == -1  # DAVI_EINVAL, nothing launched
     buf = ctypes.create_string_buffer(256)
     libdavi.davi_last_error(buf, 256)
     assert b"davi_dw_attn_fwd" in buf.value
+
+
+def test_options_are_set_through_the_abi_not_the_environment(libdavi):
+    """Implementation switches are explicit calls (atomics), never getenv."""
+    from deep_attentive_vi_b200 import _lib
+    assert libdavi.davi_get_option(_lib.OPT_DW_IMPL) == 0
+    assert libdavi.davi_set_option(_lib.OPT_DW_IMPL, 1) == 0 and libdavi.davi_get_option(_lib.OPT_DW_IMPL) == 1
+    assert libdavi.davi_set_option(_lib.OPT_DW_IMPL, 0) == 0
+    assert libdavi.davi_set_option(99, 1) == -1
+    csrc = os.path.join(ROOT, "deep_attentive_vi_b200", "csrc")
+    for f in os.listdir(csrc):
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f
 
 
 def test_validation_rejects_bad_shapes(libdavi):
@@ -74,3 +86,12 @@ def test_ops_refuse_cpu_tensors(libdavi):
         ops.dw_attn(torch.zeros(1, 2, 2, 4), torch.zeros(1, 1, 2, 2, 4), torch.zeros(1, 1, 2, 2, 4))
     with pytest.raises(_lib.DaviError):
         ops.dlm_nll(torch.zeros(1, 2, 2, 50), torch.zeros(1, 2, 2, 3))
+
+
+def test_host_convolution_refuses_cpu_tensors(libdavi):
+    """ops.conv2d_bias is part of the GPU path like every other op: no silent CPU computation."""
+    import pytest
+    import torch
+    from deep_attentive_vi_b200 import ops, _lib
+    with pytest.raises(_lib.DaviError):
+        ops.conv2d_bias(torch.zeros(1, 4, 4, 4), torch.zeros(4, 4, 1, 1), None)

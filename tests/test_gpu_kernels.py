@@ -145,9 +145,7 @@ def test_nonlocal_matches_oracle(cuda, N_hw, d, C):
 
 
 def test_nonlocal_exact_path_is_fp32_accurate(cuda, monkeypatch):
-    """DAVI_NONLOCAL_IMPL=simt is read once per process, so call the C ABI of the
-    exact kernel through a subprocess-free route: small N below the tensor-core
-    tile uses the exact path."""
+    """Small N below the tensor-core tile uses the exact CUDA-core path."""
     from deep_attentive_vi_b200 import ops
     torch.manual_seed(5)
     B, N_hw, d, C = 2, 4, 8, 12   # N = 16 < one MMA tile
@@ -242,6 +240,55 @@ def test_is_logsumexp_matches_oracle(cuda):
     got = ops.is_logsumexp(lw.to(cuda), S)
     want = torch.logsumexp(lw.double().reshape(S, B), 0)
     assert rel_err(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("n,C", [(10, 276), (15, 276), (17, 256)])
+def test_dw_attn_headline_shapes_match_oracle_on_the_bulk_copy_kernel(cuda, n, C):
+    """BASELINE config 2 (B=40, 16x16, d=20): these calls dispatch to the persistent cp.async.bulk
+    forward kernel (dw_attn_fwd_v2_kernel: n >= 8 and n*B*P >= 102400).  Forward vs the fp64 oracle
+    (att.py:135-164) at 2e-6, gradients at 1e-5, and the register-streaming kernels
+    (davi_set_option(DAVI_OPT_DW_IMPL, 1)) must give the same bits on the same inputs."""
+    from deep_attentive_vi_b200 import _lib, ops
+    B, H, W, d = 40, 16, 16, 20
+    g = torch.Generator().manual_seed(100 + n)
+    q = torch.randn(B, H, W, d, generator=g)
+    k = torch.randn(B, n, H, W, d, generator=g)
+    v = torch.randn(B, n, H, W, C, generator=g)
+    go = torch.randn(B, H, W, C, generator=g)
+    sc = torch.tensor(0.9)
+    qg, kg, vg = (t.to(cuda).requires_grad_() for t in (q, k, v))
+    out = ops.dw_attn(qg, kg, vg, sc.to(cuda))
+    out.backward(go.to(cuda))
+    want = ref.depthwise_attention_apply(q.double(), k.double(), v.double(), sc.double())
+    assert rel_err(out, want) < 2e-6
+    qr, kr, vr = (t.double().requires_grad_() for t in (q, k, v))
+    ref.depthwise_attention_apply(qr, kr, vr, sc.double()).backward(go.double())
+    assert rel_err(qg.grad, qr.grad) < 1e-5
+    assert rel_err(kg.grad, kr.grad) < 1e-5
+    assert rel_err(vg.grad, vr.grad) < 1e-5
+    _lib.set_option(_lib.OPT_DW_IMPL, 1)
+    try:
+        out_v1 = ops.dw_attn(qg.detach(), kg.detach(), vg.detach(), sc.to(cuda))
+    finally:
+        _lib.set_option(_lib.OPT_DW_IMPL, 0)
+    assert torch.equal(out.detach(), out_v1), (out.detach() - out_v1).abs().max().item()
+
+
+def test_nonlocal_forced_exact_kernels_match_tensor_core_kernels(cuda):
+    """davi_set_option(DAVI_OPT_NONLOCAL_IMPL, 1): the CUDA-core fp32 kernels on a tensor-core shape."""
+    from deep_attentive_vi_b200 import _lib, ops
+    torch.manual_seed(21)
+    B, N_hw, d, C = 2, 16, 32, 276
+    q, k = torch.randn(B, N_hw, N_hw, d, device=cuda) * 0.5, torch.randn(B, N_hw, N_hw, d, device=cuda) * 0.5
+    v, x = torch.randn(B, N_hw, N_hw, C, device=cuda), torch.randn(B, N_hw, N_hw, C, device=cuda)
+    sc, ga = torch.tensor(0.8, device=cuda), torch.tensor(0.6, device=cuda)
+    y_tc = ops.nonlocal_attn(q, k, v, x, sc, ga)
+    _lib.set_option(_lib.OPT_NONLOCAL_IMPL, 1)
+    try:
+        y_simt = ops.nonlocal_attn(q, k, v, x, sc, ga)
+    finally:
+        _lib.set_option(_lib.OPT_NONLOCAL_IMPL, 0)
+    assert rel_err(y_tc, y_simt) < 1e-5
 
 
 def test_full_size_properties_cifar_decoder_call(cuda):

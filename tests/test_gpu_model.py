@@ -152,3 +152,66 @@ def test_full_omniglot_15_layer_model_matches_oracle(cuda, convs):
                            [None if n is None else (dev(n[0]), dev(n[1])) for n in noise])
     rel = lambda a, b: ((a.double().cpu() - b).abs() / b.abs()).max().item()
     assert rel(nll, nll_o) < 1e-4 and rel(kl, kl_o) < 1e-4 and rel(nelbo, nelbo_o) < 1e-4
+
+
+def test_full_cifar10_16_layer_model_elbo_and_entire_gradient_match_oracle(cuda):
+    """BASELINE config 2 itself: the published 16-layer CIFAR-10 attentive VAE (118.97 M parameters,
+    README.md:38-48; n up to 17 slots, C = 276 / 316 / 296 nonlocal blocks, the N = 1024 pre-processor
+    blocks with the C = 138 -> 140 pad path), batch 2, default conv precision (3xTF32).  nll / sum(kl) /
+    nelbo per image at 1e-4 relative, and the ENTIRE flat gradient of the training loss -- every one of
+    the 118 966 391 parameters, as the Trainer deposits it in its flat array (hand-written backward
+    kernels, lazy gather of the shared contexts, fused weight-norm gradient) -- against autograd of the
+    fp64 oracle: 1e-4 relative to the norm of the whole gradient."""
+    from deep_attentive_vi_b200.model import CIFAR10_16L, DeepVAE, parse_flags
+    from deep_attentive_vi_b200.util.trainer import Trainer
+    kw = parse_flags(**CIFAR10_16L)
+    torch.manual_seed(0)
+    m = DeepVAE(**kw)
+    assert m.count_params() == 118966391
+    helpers.randomize_zero_init_scalars(m)
+    B = 2
+    x = helpers.synthetic_images(kw, B, seed=1000)
+    eps, noise = m.draw_noise(B, "cpu", generator=torch.Generator().manual_seed(1), training=True)
+    oracle = OracleVAE(helpers.oracle_cfg(kw), m.state_dict())
+    names = [k for k, p in m.named_parameters() if p.requires_grad]
+    for k in names:
+        oracle.sd[k].requires_grad_()
+    nll_o, kl_o, nelbo_o = oracle.forward(x, eps, True, noise)
+    beta = 0.7
+    ((nll_o.sum() + beta * kl_o.sum()) / B).backward()
+
+    m = m.to(cuda)
+    tr = Trainer(m, device=cuda, use_schedule=False)
+    tr.beta_dev.fill_(beta)
+    dev = lambda t: None if t is None else t.to(cuda)
+    nll, kl = tr.forward_backward(x.to(cuda), [dev(e) for e in eps],
+                                  [None if n is None else (dev(n[0]), dev(n[1])) for n in noise])
+    rel = lambda a, b: ((a.detach().double().cpu() - b.detach()).abs() / b.detach().abs()).max().item()
+    assert rel(nll, nll_o) < 1e-4, rel(nll, nll_o)
+    assert rel(kl, kl_o) < 1e-4, rel(kl, kl_o)
+    assert rel(nll + kl, nelbo_o) < 1e-4
+    num = den = 0.0
+    worst = (0.0, None)
+    by_name = dict(m.named_parameters())
+    covered = 0
+    for p, which, off, n, is_conv in tr.state.slots:
+        if which != "G":
+            continue
+        name = next(k for k in names if by_name[k] is p)
+        g = tr.state.G[off:off + n]
+        if is_conv:
+            o, i, h, w = p.shape
+            g = g.view(o, h, w, i).permute(0, 3, 1, 2)
+        g = g.reshape(p.shape).double().cpu()
+        go = oracle.sd[name].grad
+        go = torch.zeros_like(g) if go is None else go
+        e2, n2 = (g - go).square().sum().item(), go.square().sum().item()
+        num += e2; den += n2
+        covered += n
+        if n2 > 0 and (e2 / n2) ** 0.5 > worst[0]:
+            worst = ((e2 / n2) ** 0.5, name)
+    assert covered == sum(p.numel() for p in m.parameters() if p.requires_grad) >= 118966391
+    whole = (num / den) ** 0.5
+    print(f"CIFAR10_16L B=2: whole-gradient rel-to-norm error {whole:.3e}; worst single tensor {worst}")
+    assert whole < 1e-4, whole
+    assert worst[0] < 2e-3, worst       # single tensors with tiny norms carry the cancellation of their sums

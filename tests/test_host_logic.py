@@ -12,20 +12,30 @@ import torch.multiprocessing as mp
 import helpers
 
 
-def test_l2_classes_match_reg_loss_gradient():
-    """d reg_loss / d p == 2 * l2_coefficient(name) * p for every trainable parameter."""
+def test_regulariser_coefficients_come_from_reg_loss():
+    """The fused optimizer's per-tensor l2 strength is read off the modules' own reg_loss():
+    d reg_loss / d p == 2 * c * p for every trainable parameter, per-layer lambda_reg included, and
+    the model's weights are left untouched by the probe."""
     from deep_attentive_vi_b200.model import DeepVAE, parse_flags
-    from deep_attentive_vi_b200.util.trainer import l2_coefficient
+    from deep_attentive_vi_b200.util.trainer import regulariser_coefficients
     for flags in (helpers.SMALL_CIFAR, helpers.SMALL_OMNIGLOT):
+        flags = dict(flags)
+        flags["decoder_hparams"] = flags["decoder_hparams"] + ",lambda_reg=0.0003"    # a non-default strength
         m = DeepVAE(**parse_flags(**flags))
         helpers.randomize_zero_init_scalars(m)
+        before = {n: p.detach().clone() for n, p in m.named_parameters()}
+        coef = regulariser_coefficients(m)
+        assert all(torch.equal(before[n], p.detach()) for n, p in m.named_parameters())
         m.reg_loss().backward()
+        seen = set()
         for n, p in m.named_parameters():
             if not p.requires_grad:
                 assert p.grad is None
                 continue
-            want = 2 * l2_coefficient(n) * p.detach()
+            want = 2 * coef[p] * p.detach()
             assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-12), n
+            seen.add(round(coef[p], 9))
+        assert {round(1.5e-4, 9), round(3e-4, 9), 0.01} <= seen, seen
 
 
 def test_schedules():
@@ -33,9 +43,49 @@ def test_schedules():
     assert kl_beta(0) == pytest.approx(0.1) and kl_beta(16) == 1.0 and kl_beta(100) == 1.0
     assert kl_beta(8) == pytest.approx(0.55)
     lr = lambda s: cosine_warmup_lr(s, 100, 1e-2, 1e-4, 5, 395)
-    assert lr(0) == pytest.approx(1e-4) and lr(500) == pytest.approx(1e-2)
-    assert lr(500 + 395 * 100) == pytest.approx(1e-4)
+    assert lr(1) == pytest.approx(1e-4 + (1e-2 - 1e-4) / 500) and lr(500) == pytest.approx(1e-2)
+    assert lr(500 + 395 * 100) == pytest.approx(1e-4) and lr(10 ** 6) == pytest.approx(1e-4)
     assert lr(250) == pytest.approx(1e-4 + (1e-2 - 1e-4) * 0.5)
+
+
+def test_cosine_warmup_matches_the_reference_schedule_golden():
+    """(step -> lr) points produced by the reference's own CosineWarmup, driven like its Keras callback
+    (tests/golden/make_golden_lr.py): the host schedule reproduces every point, with the schedule lengths
+    derived like keras_train (tr.py:139-140: steps_per_epoch = int(train_size / (num_gpus * batch)),
+    decay_epochs = epochs - lr_warmup_epochs)."""
+    import json
+    from deep_attentive_vi_b200.util.trainer import cosine_warmup_lr
+    fix = json.load(open(os.path.join(helpers.GOLDEN_DIR, "ref_lr_schedule.json")))
+    assert len(fix["cases"]) >= 3
+    for c in fix["cases"]:
+        spe = int(c["train_size"] / (c["num_gpus"] * c["batch_size"]))
+        decay = c["epochs"] - c["lr_warmup_epochs"]
+        assert (spe, decay) == (c["steps_per_epoch"], c["lr_decay_epochs"])
+        for step, want in c["points"]:
+            got = cosine_warmup_lr(step, spe, c["learning_rate"], c["lr_min_learning_rate"],
+                                   c["lr_warmup_epochs"], decay)
+            assert got == pytest.approx(want, rel=1e-6), (step, got, want)
+
+
+def test_empty_sample_shards_and_rank_streams():
+    """K < world: ranks without samples contribute -inf and the combination is still the K-sample estimate;
+    ranks that share a seed draw different samples."""
+    from deep_attentive_vi_b200.util.eval import combine_partial_logsumexp, decorrelate_rank_rng, shard_samples
+    K, world = 3, 8
+    lw = torch.randn(K, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    partials = []
+    for r in range(world):
+        lo, hi = shard_samples(K, world, r)
+        partials.append(torch.logsumexp(lw[lo:hi], 0) if hi > lo else torch.full((5,), float("-inf"), dtype=torch.float64))
+    got = combine_partial_logsumexp(torch.stack(partials), K)
+    assert torch.allclose(got, torch.logsumexp(lw, 0) - math.log(K))
+    draws = []
+    for r in range(2):
+        torch.manual_seed(0)
+        decorrelate_rank_rng("cpu", r, 2)
+        draws.append(torch.randn(4))
+    torch.manual_seed(0)
+    assert not torch.equal(draws[0], draws[1])
 
 
 def test_sample_sharding_covers_all_samples():

@@ -1,5 +1,5 @@
 """Dev tool (GPU box): nonlocal attention forward/backward vs the fp64 oracle for
-the shapes of both published configs, with timings.  DAVI_NONLOCAL_IMPL=simt
+the shapes of both published configs, with timings.  --simt (davi_set_option)
 selects the exact CUDA-core kernels for comparison."""
 import json
 import os
@@ -94,7 +94,11 @@ def case(B, HW, d, C, bwd, timing=True):
 if __name__ == "__main__":
     bwd = "--bwd" in sys.argv
     small = "--small" in sys.argv
-    print(json.dumps({"impl": os.environ.get("DAVI_NONLOCAL_IMPL", "tc")}))
+    simt = "--simt" in sys.argv
+    if simt:
+        from deep_attentive_vi_b200 import _lib
+        _lib.set_option(_lib.OPT_NONLOCAL_IMPL, 1)
+    print(json.dumps({"impl": "simt" if simt else "tc"}))
     case(2, 16, 32, 64, bwd)
     if not small:
         case(40, 16, 32, 276, bwd)
