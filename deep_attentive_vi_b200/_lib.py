@@ -28,7 +28,9 @@ SIGNATURES = {
     "davi_dw_attn_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _l, _l, _f, _s]),
     "davi_dw_attn_slots_fwd": (_i, [_f, _pp, _pp, _lp, _lp, _f, _f, _i, _i, _i, _i, _i, _l, _l, _f, _s]),
     "davi_dw_attn_slots_bwd": (_i, [_f, _pp, _pp, _lp, _lp, _f, _f, _pp, _pp, _lp, _lp, _f, _i, _i, _i, _i, _i,
-                                    _l, _l, _f, ctypes.c_uint32, _s]),
+                                    _l, _l, _f, ctypes.c_uint32, _f, _f, _s]),
+    "davi_dw_attn_gather": (_i, [_i, ctypes.POINTER(ctypes.c_int), _pp, _pp, _lp, _lp, _pp, _lp, _pp, _lp, _pp, _pp,
+                                 _lp, _i, _i, _i, _i, _s]),
     "davi_ln_gelu_fwd": (_i, [_f, _f, _f, _f, _l, _i, _l, _l, _r, _i, _s]),
     "davi_ln_gelu_bwd_workspace_bytes": (_z, [_l, _i]),
     "davi_ln_gelu_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _l, _i, _l, _l, _l, _r, _i, _f, _z, _s]),
@@ -111,10 +113,23 @@ def add_launches(n):
     _launches += n
 
 
+# Measurement hook (bench.py): {"prefix": str, "events": []} brackets every call whose name starts with
+# the prefix with a pair of CUDA events on the current stream (in-step kernel time of an eager step).
+timed = None
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero code."""
     global _launches
-    check(getattr(load(), name)(*args), name)
+    if timed is not None and name.startswith(timed["prefix"]):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(load(), name)(*args), name)
+        e1.record()
+        timed["events"].append((name, e0, e1))
+    else:
+        check(getattr(load(), name)(*args), name)
     _launches += KERNELS_PER_CALL.get(name, 1)
 
 

@@ -43,6 +43,8 @@ struct DwGeom {
     int64_t q_sp, o_sp;
     uint32_t acc_mask;       // backward: bit j set = slot j's dK/dV are accumulated (+=), else overwritten
     const float* scale_ptr;  // device scalar, nullptr = 1.0
+    float* attn_out;         // backward, optional [total_pix, n]: the recomputed softmax weights a_j
+    float* ds_out;           // backward, optional [total_pix, n]: scale * ds_j (the weight of q in dK_j)
 };
 
 // per-CTA copy of the slot table with the pixel offsets of THIS thread's pixel resolved lazily
@@ -453,6 +455,16 @@ __device__ __forceinline__ void dw_attn_bwd_body(const SlotPtrs& sp, const SlotG
             ds[t] = a[t] * (da[t] - dsum);
             dsc_local += ds[t] * r[t];
         }
+        if (g.attn_out) {   // saved for the gather of the shared contexts' gradients (dw_gather_kernel)
+#pragma unroll
+            for (int t = 0; t < SPL; ++t) {
+                const int j = l + t * G;
+                if (j < g.n) {
+                    g.attn_out[(int64_t)pix * g.n + j] = a[t];
+                    g.ds_out[(int64_t)pix * g.n + j] = ds[t] * scale;
+                }
+            }
+        }
 
         // pass 2: writes.  lanes < d4 own one float4 column of q / dq / dK rows.  The key rows are
         // re-read (L1/L2 hits) in batches of UNROLL BEFORE the stores of the batch, so that the
@@ -538,6 +550,109 @@ dw_attn_bwd_small_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* 
                          const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dscale,
                          const DwGeom g) {
     dw_attn_bwd_body<G, ITERS, UNROLL>(sp, gp, q, dout, dq, dscale, g);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Gradient GATHER of the shared contexts (SURVEY.md 8f3, section 7 "backward bytes").  A context
+// c[k] is a slot of every later layer i; its gradient is
+//     dV_k = sum_i a_k^(i) * dOut^(i)          dK_k = sum_i (scale ds_k^(i)) * q^(i)
+// With the weights a^(i), scale*ds^(i) [B,P,n_i] saved by each layer's backward kernel, this is the
+// forward contraction again (a weighted sum of rows over a slot list) with GIVEN weights: every
+// gradient row is WRITTEN ONCE instead of being read-modify-written by each of the L-1-k consumers.
+// One launch handles several contexts (blockIdx.y = problem): the bottom-up tensors e[1..L] are all
+// finished by layer 0's backward and are gathered together.
+// ---------------------------------------------------------------------------------------
+constexpr int kGatherMaxProblems = 32;
+constexpr int kGatherMaxSlots = 320;
+
+struct GatherSlot {
+    const float* v;    // consumer's dOut rows [B*P, C], pixel stride v_sp
+    const float* k;    // consumer's query rows [B*P, d], pixel stride k_sp
+    const float* wa;   // consumer's a      + slot index, pixel stride wn
+    const float* wd;   // consumer's scale*ds + slot index, pixel stride wn
+    int v_sp, k_sp, wn, pad_;
+};
+struct GatherProblem {
+    float* out_v;      // [B*P, C] pixel stride ov_sp
+    float* out_k;      // [B*P, d] pixel stride ok_sp (nullable)
+    int ov_sp, ok_sp, first, m;
+};
+struct GatherParams {
+    GatherProblem prob[kGatherMaxProblems];
+    GatherSlot slot[kGatherMaxSlots];
+};
+
+template <int G, int ITERS>
+__global__ void __launch_bounds__(kDwThreads)
+dw_gather_kernel(const __grid_constant__ GatherParams gp, const int total_pix, const int d4, const int C4) {
+    constexpr int U = 4;
+    const GatherProblem& pr = gp.prob[blockIdx.y];
+    const int l = threadIdx.x & (G - 1);
+    const int pix = (blockIdx.x * kDwThreads + threadIdx.x) / G;
+    if (pix >= total_pix) return;
+    const GatherSlot* sl = gp.slot + pr.first;
+    const int m = pr.m;
+    const bool last_ok = (l + (ITERS - 1) * G) < C4;
+
+    float4 acc[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + U <= m; j += U) {
+        float4 v[U][ITERS];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const GatherSlot& s = sl[j + u];
+            w[u] = __ldg(s.wa + (int64_t)pix * s.wn);
+            const float* vp = s.v + (int64_t)pix * s.v_sp + 4 * l;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                if (it < ITERS - 1 || last_ok) v[u][it] = ld_stream4(vp + 4 * it * G);
+                else v[u][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) fma4(acc[it], w[u], v[u][it]);
+    }
+    for (; j < m; ++j) {
+        const GatherSlot& s = sl[j];
+        const float w = __ldg(s.wa + (int64_t)pix * s.wn);
+        const float* vp = s.v + (int64_t)pix * s.v_sp + 4 * l;
+        float4 v[ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            if (it < ITERS - 1 || last_ok) v[it] = ld_stream4(vp + 4 * it * G);
+            else v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) fma4(acc[it], w, v[it]);
+    }
+    float* op = pr.out_v + (int64_t)pix * pr.ov_sp + 4 * l;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+        if (it < ITERS - 1 || last_ok) st_stream4(op + 4 * it * G, acc[it]);
+
+    if (pr.out_k) {   // key part: d floats per pixel; the float4 columns are spread over the group's lanes
+        for (int c = l; c < d4; c += G) {
+            float4 kacc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int jj = 0; jj < m; ++jj) {
+                const GatherSlot& s = sl[jj];
+                fma4(kacc, __ldg(s.wd + (int64_t)pix * s.wn), ld4(s.k + (int64_t)pix * s.k_sp + 4 * c));
+            }
+            *reinterpret_cast<float4*>(pr.out_k + (int64_t)pix * pr.ok_sp + 4 * c) = kacc;
+        }
+    }
+}
+
+template <int G, int ITERS>
+static void launch_gather(const GatherParams& gp, int nprob, int total_pix, int d4, int C4, cudaStream_t st) {
+    const int64_t threads = (int64_t)total_pix * G;
+    const dim3 grid((unsigned)((threads + kDwThreads - 1) / kDwThreads), (unsigned)nprob);
+    dw_gather_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(gp, total_pix, d4, C4);
 }
 
 // ---- host-side dispatch ----------------------------------------------------
@@ -737,8 +852,10 @@ extern "C" int davi_dw_attn_slots_bwd(const float* q, const float* const* k_ptrs
                                       const float* dout, float* dq, float* const* dk_ptrs, float* const* dv_ptrs,
                                       const int64_t* dk_sps, const int64_t* dv_sps, float* dscale, int B, int n,
                                       int P, int d, int C, int64_t q_sp, int64_t o_sp, const float* scale,
-                                      uint32_t accumulate_mask, davi_stream_t stream) {
+                                      uint32_t accumulate_mask, float* attn_out, float* ds_out,
+                                      davi_stream_t stream) {
     DAVI_REQUIRE(k_ptrs && v_ptrs && k_sps && v_sps && dk_ptrs && dv_ptrs && dk_sps && dv_sps, "null slot tables");
+    DAVI_REQUIRE((attn_out == nullptr) == (ds_out == nullptr), "attn_out and ds_out come together");
     DAVI_REQUIRE(n >= 1 && n <= DAVI_MAX_SLOTS, "n out of range");
     SlotPtrs sp{}; SlotGradPtrs gp{};
     for (int j = 0; j < n; ++j) {
@@ -751,5 +868,45 @@ extern "C" int davi_dw_attn_slots_bwd(const float* q, const float* const* k_ptrs
                      "bad slot gradient strides");
     }
     DwGeom g{}; g.q_sp = q_sp; g.o_sp = o_sp; g.scale_ptr = scale; g.acc_mask = accumulate_mask;
+    g.attn_out = attn_out; g.ds_out = ds_out;
     return dw_bwd_impl(__func__, sp, gp, q, dout, dq, dscale, B, n, P, d, C, g, (cudaStream_t)stream);
+}
+
+extern "C" int davi_dw_attn_gather(int nprob, const int* m, float* const* out_v, float* const* out_k,
+                                   const int64_t* out_v_sps, const int64_t* out_k_sps,
+                                   const float* const* v_ptrs, const int64_t* v_sps,
+                                   const float* const* k_ptrs, const int64_t* k_sps,
+                                   const float* const* wa_ptrs, const float* const* wd_ptrs,
+                                   const int64_t* w_sps, int B, int P, int d, int C, davi_stream_t stream) {
+    DAVI_REQUIRE(nprob >= 1 && nprob <= kGatherMaxProblems, "1 <= nprob <= 32");
+    DAVI_REQUIRE(m && out_v && out_k && out_v_sps && out_k_sps && v_ptrs && v_sps && k_ptrs && k_sps && wa_ptrs &&
+                 wd_ptrs && w_sps, "null table");
+    DAVI_REQUIRE(B > 0 && P > 0 && d > 0 && C > 0 && !(d & 3) && !(C & 3) && d <= 128 && C <= 512, "bad d / C");
+    DAVI_REQUIRE((int64_t)B * P <= 0x7fffffff / 32, "B*P too large");
+    GatherParams gp{};
+    int tot = 0;
+    for (int p = 0; p < nprob; ++p) {
+        DAVI_REQUIRE(m[p] >= 1 && tot + m[p] <= kGatherMaxSlots, "consumer counts out of range");
+        DAVI_REQUIRE(out_v[p] && aligned16(out_v[p]) && aligned16(out_k[p]), "output pointer null / unaligned");
+        DAVI_REQUIRE(mult4(out_v_sps[p]) && out_v_sps[p] >= C && out_v_sps[p] <= 0x7fffffff &&
+                     (!out_k[p] || (mult4(out_k_sps[p]) && out_k_sps[p] >= d && out_k_sps[p] <= 0x7fffffff)),
+                     "bad output strides");
+        gp.prob[p].out_v = out_v[p]; gp.prob[p].out_k = out_k[p];
+        gp.prob[p].ov_sp = (int)out_v_sps[p]; gp.prob[p].ok_sp = out_k[p] ? (int)out_k_sps[p] : 0;
+        gp.prob[p].first = tot; gp.prob[p].m = m[p];
+        for (int j = 0; j < m[p]; ++j, ++tot) {
+            GatherSlot& s = gp.slot[tot];
+            s.v = v_ptrs[tot]; s.k = k_ptrs[tot]; s.wa = wa_ptrs[tot]; s.wd = wd_ptrs[tot];
+            DAVI_REQUIRE(s.v && s.wa && aligned16(s.v) && (!out_k[p] || (s.k && s.wd && aligned16(s.k))),
+                         "consumer pointer null / unaligned");
+            DAVI_REQUIRE(mult4(v_sps[tot]) && v_sps[tot] >= C && v_sps[tot] <= 0x7fffffff &&
+                         (!out_k[p] || (mult4(k_sps[tot]) && k_sps[tot] >= d && k_sps[tot] <= 0x7fffffff)) &&
+                         w_sps[tot] >= 1 && w_sps[tot] <= DAVI_MAX_SLOTS, "bad consumer strides");
+            s.v_sp = (int)v_sps[tot]; s.k_sp = out_k[p] ? (int)k_sps[tot] : 0; s.wn = (int)w_sps[tot];
+        }
+    }
+    DwGeom g{}; g.C4 = C / 4;
+    const int total_pix = B * P, d4 = d / 4;
+    DW_DISPATCH(launch_gather, gp, nprob, total_pix, d4, g.C4, (cudaStream_t)stream);
+    return check_launch(__func__);
 }

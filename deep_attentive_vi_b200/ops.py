@@ -122,16 +122,18 @@ def dw_attn_weights(query, keys, scale=None):
 
 class SharedSlot:
     """A per-layer tensor [B,H,W,nv+d] (values || key along the channel axis) that several LATER
-    layers attend to.  Its gradient is gathered lazily: every consumer's backward kernel adds its
-    contribution straight into one buffer (`accumulate_mask` of davi_dw_attn_slots_bwd) instead of
-    producing a zero-filled full-size slice gradient that autograd then sums (what TF's add_n over
-    the L-1 consumers does).  Exactly one consumer -- the EARLIEST layer in forward
-    order, whose backward runs last -- takes the tensor as a real autograd input ("own") and hands
-    the finished buffer back as its gradient; all later layers use it detached ("acc")."""
+    layers attend to.  Its gradient is GATHERED lazily: the backward kernel of every
+    consumer only saves its softmax weights a and scale*ds ([B,P,n], davi_dw_attn_slots_bwd attn_out /
+    ds_out) and registers itself here; when the backward of the EARLIEST consumer in forward order runs
+    (the last one to run; it takes the tensor as a real autograd input, "own"), ONE gather kernel
+    (davi_dw_attn_gather) writes the gradient once as sum_i a^(i) dOut^(i) || sum_i scale ds^(i) q^(i).
+    Neither the zero-filled slice gradients + add_n of TF autodiff nor a read-modify-write per consumer
+    exist.  All later layers use the tensor detached ("acc")."""
 
     def __init__(self, tensor, nv):
         self.tensor = tensor if tensor.is_contiguous() else tensor.contiguous()
         self.nv = nv
+        self.consumers = []     # (dout, q, q_sp, a, ds, slot index, n) of every backward that attended to it
         self.grad = None
         self.closed = False
 
@@ -158,6 +160,56 @@ def _slot_tables(spec, tensors, d, C):
     return kp, vp, ks, vs, keep
 
 
+_GATHER_MAX_PROBLEMS, _GATHER_MAX_SLOTS = 32, 320      # kGatherMaxProblems / kGatherMaxSlots of dw_attn.cu
+
+# Measurement hook (bench.py): when a list, every depth-wise attention launch appends the STRUCTURE of its
+# call (shapes, per-slot strides, which gradients are written / skipped / gathered) so that exactly the
+# launches of one training step can be replayed on synthetic operands (tools/dw_replay.py).
+dw_trace = None
+
+
+def _trace_slots(kp, vp, ks, vs):
+    out = []
+    for k, v, k_s, v_s in zip(kp, vp, ks, vs):
+        koff = (k - v) // 4
+        out.append({"k_sp": int(k_s), "v_sp": int(v_s), "koff": int(koff) if 0 <= koff < v_s else None})
+    return out
+
+
+def _gather_shared(owned, B, P, d, C):
+    """davi_dw_attn_gather over the shared contexts whose last consumer just ran: one launch for as many
+    contexts as fit its tables (the bottom-up tensors e[1..L] all finish in layer 0's backward)."""
+    import ctypes
+    batch, tot = [], 0
+    batches = [batch]
+    for sh in owned:
+        m = len(sh.consumers)
+        assert m <= _GATHER_MAX_SLOTS
+        if len(batch) == _GATHER_MAX_PROBLEMS or tot + m > _GATHER_MAX_SLOTS:
+            batch, tot = [], 0
+            batches.append(batch)
+        batch.append(sh); tot += m
+    for batch in batches:
+        ms, ov, ok, ovs, oks, vp, vs, kp, ks, wa, wd, ws = ([] for _ in range(12))
+        for sh in batch:
+            ct = sh.tensor.shape[-1]
+            ms.append(len(sh.consumers))
+            ov.append(sh.grad.data_ptr()); ok.append(sh.grad.data_ptr() + 4 * sh.nv); ovs.append(ct); oks.append(ct)
+            for dout, q, q_sp, a, ds, j, n in sh.consumers:
+                vp.append(dout.data_ptr()); vs.append(C); kp.append(q.data_ptr()); ks.append(q_sp)
+                wa.append(a.data_ptr() + 4 * j); wd.append(ds.data_ptr() + 4 * j); ws.append(n)
+        mt = (ctypes.c_int * len(ms))(*ms)
+        tabs = [_lib.ptr_table(ov), _lib.ptr_table(ok), _lib.int_table(ovs), _lib.int_table(oks),
+                _lib.ptr_table(vp), _lib.int_table(vs), _lib.ptr_table(kp), _lib.int_table(ks),
+                _lib.ptr_table(wa), _lib.ptr_table(wd), _lib.int_table(ws)]
+        _lib_call("davi_dw_attn_gather", len(ms), mt, *[t[0] for t in tabs], B, P, d, C, _stream())
+        if dw_trace is not None:
+            dw_trace.append({"op": "gather", "B": B, "P": P, "d": d, "C": C,
+                             "problems": [{"ct": int(sh.tensor.shape[-1]), "nv": int(sh.nv),
+                                           "consumers": [{"n": int(c[6]), "j": int(c[5]), "q_sp": int(c[2])}
+                                                         for c in sh.consumers]} for sh in batch]})
+
+
 class _DwAttnSlots(torch.autograd.Function):
     """inputs: query, scale, spec, then the autograd-visible tensors named by spec:
     ("kv",) -> key, value;  ("own", shared) -> shared.tensor;  ("acc", shared) -> nothing."""
@@ -180,6 +232,9 @@ class _DwAttnSlots(torch.autograd.Function):
         vst, vsa = _lib.int_table(vs)
         _lib_call("davi_dw_attn_slots_fwd", _p(q), kt, vt, kst, vst, _p(out), 0, B, n, P, d, C,
                   q_sp, C, s_ptr, _stream())
+        if dw_trace is not None:
+            dw_trace.append({"op": "fwd", "B": B, "n": n, "P": P, "d": d, "C": C, "q_sp": int(q_sp),
+                             "slots": _trace_slots(kp, vp, ks, vs)})
         ctx.save_for_backward(q, s_t, *keep)
         ctx.spec = spec
         ctx.dims = (B, n, P, d, C, q_sp, kp, vp, ks, vs)
@@ -199,27 +254,33 @@ class _DwAttnSlots(torch.autograd.Function):
             q = q.contiguous(); q_sp = d
         need_ds = s_t is not None and ctx.needs_input_grad[1]
         dscale = torch.empty((), device=dev, dtype=torch.float32) if need_ds else None
-        dkp, dvp, dks, dvs, grads, mask = [], [], [], [], [], 0
+        dkp, dvp, dks, dvs, grads, owned = [], [], [], [], [], []
         lead = dout.shape[:-1]
+        a_out = ds_out = None
+        if any(item[0] != "kv" for item in spec):
+            a_out = torch.empty((B * P, n), device=dev, dtype=torch.float32)
+            ds_out = torch.empty((B * P, n), device=dev, dtype=torch.float32)
         for j, item in enumerate(spec):
             if item[0] == "kv":
                 dk = torch.empty((*lead, d), device=dev, dtype=torch.float32)
                 dv = torch.empty((*lead, C), device=dev, dtype=torch.float32)
                 grads += [dk, dv]
                 dkp.append(dk.data_ptr()); dvp.append(dv.data_ptr()); dks.append(d); dvs.append(C)
-            else:
-                sh = item[1]
-                assert not sh.closed, "shared context consumed after its owner's backward ran"
-                if sh.grad is None:
-                    sh.grad = torch.empty_like(sh.tensor)            # first touch overwrites: no memset
-                else:
-                    mask |= 1 << j
-                ct = sh.tensor.shape[-1]
-                dkp.append(sh.grad.data_ptr() + 4 * sh.nv); dvp.append(sh.grad.data_ptr())
-                dks.append(ct); dvs.append(ct)
-                if item[0] == "own":
-                    grads.append(sh.grad)
-                    sh.closed = True
+                continue
+            sh = item[1]
+            assert not sh.closed, "shared context consumed after its owner's backward ran"
+            ct = sh.tensor.shape[-1]
+            if item[0] == "own":
+                sh.grad = torch.empty_like(sh.tensor)                # every row is written once: no memset
+                sh.closed = True
+                grads.append(sh.grad)
+                if not sh.consumers:                                 # sole consumer: this kernel writes it directly
+                    dkp.append(sh.grad.data_ptr() + 4 * sh.nv); dvp.append(sh.grad.data_ptr())
+                    dks.append(ct); dvs.append(ct)
+                    continue
+                owned.append(sh)
+            sh.consumers.append((dout, q, q_sp, a_out, ds_out, j, n))
+            dkp.append(0); dvp.append(0); dks.append(ct); dvs.append(ct)   # NULL: gathered later
         kt, ka = _lib.ptr_table(kp)
         vt, va = _lib.ptr_table(vp)
         kst, ksa = _lib.int_table(ks)
@@ -229,7 +290,17 @@ class _DwAttnSlots(torch.autograd.Function):
         dkst, dksa = _lib.int_table(dks)
         dvst, dvsa = _lib.int_table(dvs)
         _lib_call("davi_dw_attn_slots_bwd", _p(q), kt, vt, kst, vst, _p(dout), _p(dq), dkt, dvt, dkst, dvst,
-                  _p(dscale), B, n, P, d, C, q_sp, C, _p(s_t), mask, _stream())
+                  _p(dscale), B, n, P, d, C, q_sp, C, _p(s_t), 0, _p(a_out), _p(ds_out), _stream())
+        if dw_trace is not None:
+            dw_trace.append({"op": "bwd", "B": B, "n": n, "P": P, "d": d, "C": C, "q_sp": int(q_sp),
+                             "slots": _trace_slots(kp, vp, ks, vs), "save": a_out is not None,
+                             "grads": [None if dv == 0 else {"k_sp": int(a), "v_sp": int(b),
+                                                             "koff": int((dk - dv) // 4) if 0 <= (dk - dv) // 4 < b else None}
+                                       for dk, dv, a, b in zip(dkp, dvp, dks, dvs)]})
+        if owned:
+            _gather_shared(owned, B, P, d, C)
+            for sh in owned:
+                sh.consumers = []                                    # release the consumers' tensors
         return (dq_view, dscale, None, *grads)
 
 

@@ -122,7 +122,11 @@ int davi_dw_attn_slots_fwd(const float* q, const float* const* k_ptrs,
  * OVERWRITTEN, or read-modify-written (+=) when bit j of accumulate_mask is set:
  * one gradient buffer per context then collects the contributions of every
  * later layer directly (replaces TF's add_n over the L-1 consumers and the
- * zero-filled slice gradients).  A NULL entry skips that slot. */
+ * zero-filled slice gradients).  A NULL entry skips that slot.
+ * attn_out / ds_out (both or neither, nullable) [B,P,n] dense: the recomputed softmax
+ * weights a_j and scale * ds_j.  With them the gradient of a context that MANY layers share
+ * is not accumulated at all: its slot is passed as NULL here and davi_dw_attn_gather below
+ * writes it once from the saved weights of all its consumers. */
 int davi_dw_attn_slots_bwd(const float* q, const float* const* k_ptrs,
                            const float* const* v_ptrs,
                            const int64_t* k_sps, const int64_t* v_sps,
@@ -132,7 +136,25 @@ int davi_dw_attn_slots_bwd(const float* q, const float* const* k_ptrs,
                            float* dscale,
                            int B, int n, int P, int d, int C,
                            int64_t q_sp, int64_t o_sp,
-                           const float* scale, uint32_t accumulate_mask, davi_stream_t stream);
+                           const float* scale, uint32_t accumulate_mask,
+                           float* attn_out, float* ds_out, davi_stream_t stream);
+
+/* Gradient gather of shared contexts (the lazy gather of SURVEY.md section 7 / 8f3; replaces TF's
+ * add_n over the consumers of c[k] / e[j], model/vae.py:339-350).  Problem p (one context) has
+ * m[p] consumers; consumer t of the concatenated tables (problem-major) contributes
+ *     out_v[p][pix,:C] += wa_ptrs[t][pix * w_sps[t]] * v_ptrs[t][pix * v_sps[t] + :C]   (dOut of that layer)
+ *     out_k[p][pix,:d] += wd_ptrs[t][pix * w_sps[t]] * k_ptrs[t][pix * k_sps[t] + :d]   (its query)
+ * where wa / wd point at column j of that layer's attn_out / ds_out (j = the context's slot index
+ * there, w_sps = its n).  Every output row is written exactly once (no read-modify-write, no
+ * memset); out_k[p] may be NULL.  All tables are HOST arrays.  nprob <= 32, sum m <= 320. */
+int davi_dw_attn_gather(int nprob, const int* m,
+                        float* const* out_v, float* const* out_k,
+                        const int64_t* out_v_sps, const int64_t* out_k_sps,
+                        const float* const* v_ptrs, const int64_t* v_sps,
+                        const float* const* k_ptrs, const int64_t* k_sps,
+                        const float* const* wa_ptrs, const float* const* wd_ptrs,
+                        const int64_t* w_sps,
+                        int B, int P, int d, int C, davi_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * R2/R3 glue: LayerNormalization(epsilon) over the last axis, optionally with

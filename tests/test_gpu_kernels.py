@@ -464,3 +464,73 @@ def test_ln_gelu_residual_fused_with_gamma_matches_oracle(cuda):
     assert rel_err(y, want) < 1e-6
     for got, w, name in zip(ins, r, "x ln_gamma ln_beta base res_gamma".split()):
         assert rel_err(got.grad, w.grad) < 2e-5, name
+
+
+def test_dw_attn_gather_matches_fp64_sum(cuda):
+    """davi_dw_attn_gather on its own: several contexts (problems) with different consumer counts in ONE
+    launch, consumers with different slot counts / indices; out_v = sum_i a^(i)[:, j_i] dOut^(i),
+    out_k = sum_i wd^(i)[:, j_i] q^(i), against the same sums in fp64.  Also more problems than one
+    launch's table holds (the host side splits them)."""
+    from deep_attentive_vi_b200 import ops
+    torch.manual_seed(31)
+    B, H, W, d, C = 3, 6, 5, 20, 276            # 90 pixels: partial CTA
+    P = H * W
+    for nprob, max_m in ((5, 9), (40, 12)):
+        owned, want = [], []
+        for p in range(nprob):
+            sh = ops.SharedSlot(torch.zeros(B, H, W, C + d, device=cuda), C)
+            sh.grad = torch.full_like(sh.tensor, float("nan"))           # every element must be overwritten
+            wv = torch.zeros(B * P, C, dtype=torch.float64)
+            wk = torch.zeros(B * P, d, dtype=torch.float64)
+            for i in range(1 + (p * 7) % max_m):
+                n = 1 + (3 * i + p) % 17
+                j = (i + p) % n
+                dout = torch.randn(B, H, W, C, device=cuda)
+                q = torch.randn(B, H, W, d, device=cuda)
+                a, ds = torch.rand(B * P, n, device=cuda), torch.randn(B * P, n, device=cuda)
+                sh.consumers.append((dout, q, d, a, ds, j, n))
+                wv += a[:, j:j + 1].double().cpu() * dout.reshape(-1, C).double().cpu()
+                wk += ds[:, j:j + 1].double().cpu() * q.reshape(-1, d).double().cpu()
+            owned.append(sh); want.append(torch.cat([wv, wk], 1))
+        ops._gather_shared(owned, B, P, d, C)
+        for sh, w in zip(owned, want):
+            assert rel_err(sh.grad.reshape(-1, C + d), w) < 2e-6
+
+
+def test_dw_attn_backward_saves_weights_for_the_gather(cuda):
+    """davi_dw_attn_slots_bwd attn_out / ds_out == softmax weights and scale * ds of the fp64 oracle; slots
+    passed as NULL are skipped."""
+    from deep_attentive_vi_b200 import _lib
+    torch.manual_seed(32)
+    B, n, P, d, C = 2, 6, 64, 20, 276
+    q, k, v, go = (torch.randn(*s, device=cuda) for s in ((B, P, d), (B, n, P, d), (B, n, P, C), (B, P, C)))
+    scale = torch.tensor(0.8, device=cuda)
+    dq = torch.empty_like(q)
+    dk, dv = torch.full_like(k, 7.0), torch.full_like(v, 7.0)
+    a_out, ds_out = torch.empty(B * P, n, device=cuda), torch.empty(B * P, n, device=cuda)
+    kp = [k[:, j].contiguous() for j in range(n)]
+    vp = [v[:, j].contiguous() for j in range(n)]
+    dkj = [torch.full((B, P, d), 7.0, device=cuda) for _ in range(n)]
+    dvj = [torch.full((B, P, C), 7.0, device=cuda) for _ in range(n)]
+    skip = {1, 4}
+    T, I = _lib.ptr_table, _lib.int_table
+    tabs = [T([t.data_ptr() for t in kp]), T([t.data_ptr() for t in vp]), I([d] * n), I([C] * n),
+            T([0 if j in skip else dkj[j].data_ptr() for j in range(n)]),
+            T([0 if j in skip else dvj[j].data_ptr() for j in range(n)]), I([d] * n), I([C] * n)]
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("davi_dw_attn_slots_bwd", q.data_ptr(), tabs[0][0], tabs[1][0], tabs[2][0], tabs[3][0], go.data_ptr(),
+              dq.data_ptr(), tabs[4][0], tabs[5][0], tabs[6][0], tabs[7][0], 0, B, n, P, d, C, d, C,
+              scale.data_ptr(), 0, a_out.data_ptr(), ds_out.data_ptr(), st)
+    qd, kd, vd, gd = (t.double().cpu() for t in (q, k, v, go))
+    s = 0.8 * torch.einsum("bpd,bnpd->bpn", qd, kd)
+    a = torch.softmax(s, -1)
+    da = torch.einsum("bnpc,bpc->bpn", vd, gd)
+    ds = a * (da - (a * da).sum(-1, keepdim=True))
+    assert rel_err(a_out.reshape(B, P, n), a) < 2e-6
+    assert rel_err(ds_out.reshape(B, P, n), 0.8 * ds) < 1e-5
+    for j in range(n):
+        if j in skip:
+            assert torch.all(dvj[j] == 7.0) and torch.all(dkj[j] == 7.0)
+        else:
+            assert rel_err(dvj[j], a[..., j:j + 1] * gd) < 1e-5
+            assert rel_err(dkj[j], 0.8 * ds[..., j:j + 1] * qd) < 1e-5

@@ -64,7 +64,8 @@ def test_elbo_and_gradients_match_oracle(cuda, flags, convs):
     for k in probes:
         g, go = params[k].grad.double().cpu(), oracle.sd[k].grad
         err = (g - go).norm() / go.norm().clamp_min(1e-30)
-        assert err < 1e-3, (k, err.item())
+        print(f"probe {k}: rel-to-norm {err.item():.3e}")
+        assert err < 1e-4, (k, err.item())      # gradients 1e-4 relative to the norm
 
 
 def test_importance_sampled_chunk_matches_oracle(cuda, convs):
@@ -191,7 +192,7 @@ def test_full_cifar10_16_layer_model_elbo_and_entire_gradient_match_oracle(cuda)
     assert rel(kl, kl_o) < 1e-4, rel(kl, kl_o)
     assert rel(nll + kl, nelbo_o) < 1e-4
     num = den = 0.0
-    worst = (0.0, None)
+    per_tensor = []
     by_name = dict(m.named_parameters())
     covered = 0
     for p, which, off, n, is_conv in tr.state.slots:
@@ -208,10 +209,14 @@ def test_full_cifar10_16_layer_model_elbo_and_entire_gradient_match_oracle(cuda)
         e2, n2 = (g - go).square().sum().item(), go.square().sum().item()
         num += e2; den += n2
         covered += n
-        if n2 > 0 and (e2 / n2) ** 0.5 > worst[0]:
-            worst = ((e2 / n2) ** 0.5, name)
+        per_tensor.append((e2 ** 0.5, n2 ** 0.5, name))
     assert covered == sum(p.numel() for p in m.parameters() if p.requires_grad) >= 118966391
     whole = (num / den) ** 0.5
-    print(f"CIFAR10_16L B=2: whole-gradient rel-to-norm error {whole:.3e}; worst single tensor {worst}")
+    # per tensor: error against the tensor's own norm, for every tensor that carries a visible share of the
+    # gradient (>= 1e-4 of its norm).  Below that are gradients that are zero in exact arithmetic (the key
+    # bias of a nonlocal block shifts all logits of a row equally: fp64 autograd returns 1e-20 noise for it).
+    big = sorted(((e / n, name, n) for e, n, name in per_tensor if n >= 1e-4 * den ** 0.5), reverse=True)
+    print(f"CIFAR10_16L B=2: whole-gradient rel-to-norm error {whole:.3e} over {len(per_tensor)} tensors; "
+          f"worst of the {len(big)} tensors with >= 1e-4 of the norm: {big[:5]}")
     assert whole < 1e-4, whole
-    assert worst[0] < 2e-3, worst       # single tensors with tiny norms carry the cancellation of their sums
+    assert big[0][0] < 1e-3, big[:5]
