@@ -228,12 +228,32 @@ def dw_roofline_of_step(trainer, x, device):
     by_name = {}
     for name, e0, e1 in events:
         by_name[name] = by_name.get(name, 0.0) + e0.elapsed_time(e1)
+    # The event pairs also contain each launch's latency (~10 us per pair on these 13-60 us kernels), so the
+    # kernels' own durations inside a step are read from a CUPTI activity trace of one more eager step
+    # (torch.profiler, kernel records only) -- the per-kernel table VERDICT r01 computed its 0.44 from.
+    kern_ms, kern_by_name = None, {}
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            trainer._step_body(x)
+            torch.cuda.synchronize()
+        for ev in prof.key_averages():
+            if "davi::dw_" in ev.key:
+                us = getattr(ev, "self_device_time_total", None)
+                if us is None:
+                    us = getattr(ev, "self_cuda_time_total", 0.0)
+                short = ev.key.split("davi::")[1].split("(")[0]
+                kern_by_name[short] = {"ms": us / 1e3, "launches": ev.count}
+        kern_ms = sum(v["ms"] for v in kern_by_name.values())
+    except Exception as exc:                                  # CUPTI unavailable: the event numbers remain
+        kern_by_name = {"error": repr(exc)}
     alg = sum(dw_replay.algorithmic_bytes(e) for e in trace)
     moved = sum(dw_replay.moved_bytes(e) for e in trace)
     tb, tt, per = dw_replay.replay_roofline(trace, device)
     assert tb == alg
     return {"trace": trace, "launches": len(trace), "algorithmic_bytes": alg, "moved_bytes": moved,
-            "in_step_ms": in_step_ms, "in_step_ms_by_entry_point": by_name, "stand_alone_ms": tt, "per_launch": per}
+            "in_step_ms": in_step_ms, "in_step_ms_by_entry_point": by_name, "in_step_kernel_ms": kern_ms,
+            "in_step_kernels": kern_by_name, "stand_alone_ms": tt, "per_launch": per}
 
 
 def ncu_traffic():
@@ -274,20 +294,17 @@ def elbo_roofline(batch, device):
         post, prior, eps = (torch.randn(B, P, 2 * z, device=device), torch.randn(B, P, 2 * z, device=device),
                             torch.randn(B, P, z, device=device))
         n1, n2 = torch.randn(B, P, z, device=device), torch.randn(B, P, z, device=device)
-        xi, kl = torch.empty(B, P, z, device=device), torch.empty(B, device=device)
+        xi, kl, grad = torch.empty(B, P, z, device=device), torch.empty(B, device=device), torch.empty(B, P, 6 * z, device=device)
         return lambda: _lib.call("davi_gauss_kl_fwd", post.data_ptr(), prior.data_ptr(), eps.data_ptr(), n1.data_ptr(),
                                  n2.data_ptr(), xi.data_ptr(), kl.data_ptr(), 0, 0, B, P, z, -5.0, 5.0, -1.0, 5.0,
-                                 1e-3, 1e-3, stream)
+                                 1e-3, 1e-3, grad.data_ptr(), stream)
 
     def kl_bwd():
-        post, prior, eps = (torch.randn(B, P, 2 * z, device=device), torch.randn(B, P, 2 * z, device=device),
-                            torch.randn(B, P, z, device=device))
-        n1, n2 = torch.randn(B, P, z, device=device), torch.randn(B, P, z, device=device)
+        grad = torch.randn(B, P, 6 * z, device=device)
         dxi, dkl = torch.randn(B, P, z, device=device), torch.randn(B, device=device)
-        dpost, dprior = torch.empty_like(post), torch.empty_like(prior)
-        return lambda: _lib.call("davi_gauss_kl_bwd", post.data_ptr(), prior.data_ptr(), eps.data_ptr(), n1.data_ptr(),
-                                 n2.data_ptr(), dxi.data_ptr(), dkl.data_ptr(), dpost.data_ptr(), dprior.data_ptr(),
-                                 B, P, z, -5.0, 5.0, -1.0, 5.0, 1e-3, 1e-3, stream)
+        dpost, dprior = torch.empty(B, P, 2 * z, device=device), torch.empty(B, P, 2 * z, device=device)
+        return lambda: _lib.call("davi_gauss_kl_bwd_saved", grad.data_ptr(), dxi.data_ptr(), dkl.data_ptr(),
+                                 dpost.data_ptr(), dprior.data_ptr(), B, P, z, stream)
 
     def dlm():
         params = torch.randn(B, 1024, 50, device=device)
@@ -296,7 +313,7 @@ def elbo_roofline(batch, device):
         return lambda: _lib.call("davi_dlm_nll_fwd", params.data_ptr(), x.data_ptr(), nll.data_ptr(), g.data_ptr(),
                                  B, 1024, -7.0, stream)
 
-    for name, make, nbytes in (("gauss_kl_fwd", kl_fwd, 4 * B * P * z * 8), ("gauss_kl_bwd", kl_bwd, 4 * B * P * z * 12),
+    for name, make, nbytes in (("gauss_kl_fwd+grad", kl_fwd, 4 * B * P * z * 14), ("gauss_kl_bwd_saved", kl_bwd, 4 * B * P * z * 11),
                                ("dlm_nll_fwd+grad", dlm, 4 * B * 1024 * (50 + 3 + 50))):
         t = rot(make, nbytes)
         out[name] = {"us": round(t * 1e3, 2), "MB": round(nbytes / 1e6, 2), "GBs": round(nbytes / t / 1e6)}
@@ -533,6 +550,7 @@ def run_davi(args):
             alg = dw["algorithmic_bytes"]
             ach_alone = alg / dw["stand_alone_ms"] / 1e6
             ach_step = alg / dw["in_step_ms"] / 1e6
+            ach_kern = alg / dw["in_step_kernel_ms"] / 1e6 if dw["in_step_kernel_ms"] else None
             tr = ncu_traffic()
             line["roofline"] = {
                 "bound": "hbm",
@@ -541,10 +559,15 @@ def run_davi(args):
                 # headline fraction: the recorded launches replayed stand-alone on cold operands (rotating sets > 3x L2)
                 "achieved": ach_alone, "peak": peak, "unit": "GB/s", "frac": ach_alone / peak,
                 "frac_of_nominal_8TBs": ach_alone / 8000.0, "peak_source": which,
-                # the same launches timed INSIDE an eager step (CUDA-event pair around each: includes ~2 us of event
-                # granularity per launch, operands partly L2-resident from the producing kernels)
-                "in_step": {"achieved": ach_step, "frac": ach_step / peak, "kernel_ms_per_step": dw["in_step_ms"],
-                            "ms_by_entry_point": dw["in_step_ms_by_entry_point"]},
+                # the same launches INSIDE an eager step, operands as the neighbouring kernels left them: kernel durations
+                # from a CUPTI activity trace (`frac`), and CUDA-event pairs around each launch (`event_pairs`: an upper
+                # bound on time, every pair also holds the launch latency)
+                "in_step": {"achieved": ach_kern, "frac": ach_kern / peak if ach_kern else None,
+                            "kernel_ms_per_step": dw["in_step_kernel_ms"], "kernels": dw["in_step_kernels"],
+                            "timing": "kernel records of a CUPTI activity trace (torch.profiler) of one eager step",
+                            "event_pairs": {"achieved": ach_step, "frac": ach_step / peak,
+                                            "ms_per_step": dw["in_step_ms"],
+                                            "ms_by_entry_point": dw["in_step_ms_by_entry_point"]}},
                 "algorithmic_MB_per_step": alg / 1e6, "moved_MB_per_step": dw["moved_bytes"] / 1e6,
                 "kernel_ms_per_step": dw["stand_alone_ms"],
                 "traffic": tr["traffic_bytes_per_launch_sum"] if tr else None,

@@ -39,7 +39,8 @@ SIGNATURES = {
     "davi_nonlocal_attn_fwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _f, _f, _s]),
     "davi_nonlocal_attn_bwd_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "davi_nonlocal_attn_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _l, _l, _l, _l, _l, _f, _f, _f, _z, _s]),
-    "davi_gauss_kl_fwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _r, _r, _r, _r, _r, _r, _s]),
+    "davi_gauss_kl_fwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _r, _r, _r, _r, _r, _r, _f, _s]),
+    "davi_gauss_kl_bwd_saved": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _s]),
     "davi_gauss_kl_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _r, _r, _r, _r, _r, _r, _s]),
     "davi_dlm_nll_fwd": (_i, [_f, _f, _f, _f, _i, _i, _r, _s]),
     "davi_bernoulli_nll_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _s]),

@@ -63,7 +63,7 @@ constexpr int kDwUnroll = 4;  // slots whose value rows are in flight together
 template <int G, int SPL>
 __device__ __forceinline__ void dw_scores(const SlotTable& tb, const DwGeom& g, int l,
                                           int b, int p, const float* qp, float (&a)[SPL],
-                                          float* r_raw, unsigned gm, float scale) {
+                                          float* r_raw, unsigned gm, float scale, float* k_stash = nullptr) {
     float s[SPL];
     float m = -INFINITY;
 #pragma unroll
@@ -73,6 +73,13 @@ __device__ __forceinline__ void dw_scores(const SlotTable& tb, const DwGeom& g, 
         if (j < g.n) {
             const float* kp = tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j];
             float dot = 0.f;
+            if (k_stash) {      // keep this pixel's key rows on chip for the dq / dK phase: [slot][d]
+                for (int c = 0; c < g.d4; ++c) {
+                    const float4 kv = ld4(kp + 4 * c);
+                    *reinterpret_cast<float4*>(k_stash + (j * g.d4 + c) * 4) = kv;
+                    dot += dot4(kv, ld4(qp + 4 * c));
+                }
+            } else
             for (int c = 0; c < g.d4; ++c) dot += dot4(ld4(kp + 4 * c), ld4(qp + 4 * c));
             if (r_raw) r_raw[t] = dot;
             s[t] = dot * scale;
@@ -270,20 +277,21 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
         tb.v_sb[j] = sp.v_sb[j]; tb.v_sp[j] = sp.v_sp[j];
     }
     if (tid == 0) {
-        for (int s = 0; s < kV2Stages; ++s) { v2_mbar_init(&bars.v_full[s], 1); v2_mbar_init(&bars.v_empty[s], 128); }
+        for (int s = 0; s < kV2Stages; ++s) { v2_mbar_init(&bars.v_full[s], 1); v2_mbar_init(&bars.v_empty[s], 4); }
         for (int i = 0; i < 2; ++i) { v2_mbar_init(&bars.a_full[i], 128); v2_mbar_init(&bars.a_empty[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == 0) {
-        // ---------------- producer: one thread issues every bulk copy ----------------
-        if (tid == 0) {
+        // ---------------- producer warp: lane s issues every bulk copy into ring stage s ----------------
+        {
             uint32_t gc = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const int pix0 = t * kV2TP;
                 const int b = pix0 / g.P, p0 = pix0 - b * g.P;
                 for (int j = 0; j < g.n; ++j, ++gc) {
+                    if ((gc % kV2Stages) != (uint32_t)tid) continue;   // one lane per ring stage: its uses stay ordered
                     const int s = gc % kV2Stages;
                     if (gc >= kV2Stages) v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1);
                     const int vsp = tb.v_sp[j];
@@ -347,7 +355,8 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
 #pragma unroll
                 for (int i = 0; i < ITERS; ++i)
                     if (i < ITERS - 1 || last_ok) fma4(acc[i], aj, *reinterpret_cast<const float4*>(row + 4 * i * G));
-                v2_mbar_arrive(&bars.v_empty[s]);
+                __syncwarp();                                  // one arrival per warp: all lanes have read the stage
+                if ((tid & 31) == 0) v2_mbar_arrive(&bars.v_empty[s]);
             }
             v2_mbar_arrive(&bars.a_empty[buf]);
             float* op = out + (int64_t)(t * kV2TP + pixel) * g.o_sp + 4 * l;
@@ -552,6 +561,249 @@ dw_attn_bwd_small_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* 
     dw_attn_bwd_body<G, ITERS, UNROLL>(sp, gp, q, dout, dq, dscale, g);
 }
 
+
+
+// ---------------------------------------------------------------------------------------
+// Backward, version 2: the same persistent bulk-copy pipeline for the gradient (n >= 8, large calls).
+// Per tile of 8 pixels the producer thread stages the dOut tile and then the n value tiles; the four
+// "stream" warps take <V_j, g> of every staged tile (da_j, reduced over the 16 lanes of a pixel) and
+// write dV_j = a_j g for the slots whose gradient this launch owns; the four "score" warps recompute
+// the softmax of the NEXT tile while the current one streams and then finish the previous one from
+// da: ds_j = a_j (da_j - sum a da), dq, dK_j, the saved a / scale*ds for the gather, dscale.
+// No read-modify-write variant: accumulate masks stay on the register-streaming kernel.
+// ---------------------------------------------------------------------------------------
+struct V2BwdBars {
+    uint64_t v_full[kV2Stages], v_empty[kV2Stages];
+    uint64_t a_full[2], a_empty[2], da_full[2], da_empty[2];
+};
+
+template <int ITERS>
+__global__ void __launch_bounds__(kV2Threads, 1)
+dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __restrict__ q,
+                      const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dscale,
+                      const DwGeom g, const int ntiles) {
+    constexpr int G = 16, SPL = DAVI_MAX_SLOTS / G;
+    extern __shared__ __align__(128) uint8_t v2_smem[];
+    __shared__ SlotTable tb;
+    __shared__ SlotGradPtrs tg;
+    __shared__ V2BwdBars bars;
+    __shared__ float s_a[2][kV2TP][DAVI_MAX_SLOTS];
+    __shared__ float s_da[2][kV2TP][DAVI_MAX_SLOTS];
+    const int C = g.C4 * 4;
+    const int stage_floats = kV2TP * (C + kV2Slack);
+    float* ring = reinterpret_cast<float*>(v2_smem);
+    // key rows of the two tiles in flight: [2][kV2TP][n][d], written by the softmax phase, read by the finish phase
+    const int kst_pixel = g.n * g.d4 * 4;
+    float* kstash = ring + (size_t)kV2Stages * stage_floats;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid < DAVI_MAX_SLOTS) {
+        const int j = tid;
+        tb.k[j] = sp.k[j]; tb.v[j] = sp.v[j];
+        tb.k_sb[j] = sp.k_sb[j]; tb.k_sp[j] = sp.k_sp[j];
+        tb.v_sb[j] = sp.v_sb[j]; tb.v_sp[j] = sp.v_sp[j];
+        tg.dk[j] = gp.dk[j]; tg.dv[j] = gp.dv[j];
+        tg.k_sb[j] = gp.k_sb[j]; tg.k_sp[j] = gp.k_sp[j];
+        tg.v_sb[j] = gp.v_sb[j]; tg.v_sp[j] = gp.v_sp[j];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kV2Stages; ++s) { v2_mbar_init(&bars.v_full[s], 1); v2_mbar_init(&bars.v_empty[s], 4); }
+        for (int i = 0; i < 2; ++i) {
+            v2_mbar_init(&bars.a_full[i], 128); v2_mbar_init(&bars.a_empty[i], 128);
+            v2_mbar_init(&bars.da_full[i], 128); v2_mbar_init(&bars.da_empty[i], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer warp: per tile the dOut tile, then the n value tiles; lane s issues
+        // every bulk copy into ring stage s ----------------
+        {
+            uint32_t gc = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int pix0 = t * kV2TP;
+                const int b = pix0 / g.P, p0 = pix0 - b * g.P;
+                for (int j = -1; j < g.n; ++j, ++gc) {
+                    if ((gc % kV2Stages) != (uint32_t)tid) continue;   // one lane per ring stage: its uses stay ordered
+                    const int s = gc % kV2Stages;
+                    if (gc >= kV2Stages) v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1);
+                    float* dst = ring + (size_t)s * stage_floats;
+                    if (j < 0) {                          // dOut rows: dense stride o_sp
+                        const int osp = (int)g.o_sp;
+                        const float* src = dout + (int64_t)pix0 * osp;
+                        if (v2_single_span(osp, C)) {
+                            const uint32_t bytes = (uint32_t)((kV2TP - 1) * osp + C) * 4u;
+                            v2_mbar_expect_tx(&bars.v_full[s], bytes);
+                            v2_bulk_load(dst, src, bytes, &bars.v_full[s]);
+                        } else {
+                            v2_mbar_expect_tx(&bars.v_full[s], (uint32_t)(kV2TP * C) * 4u);
+                            for (int r = 0; r < kV2TP; ++r)
+                                v2_bulk_load(dst + r * C, src + (int64_t)r * osp, (uint32_t)C * 4u, &bars.v_full[s]);
+                        }
+                        continue;
+                    }
+                    const int vsp = tb.v_sp[j];
+                    const float* src = tb.v[j] + (int64_t)b * tb.v_sb[j] + (int64_t)p0 * vsp;
+                    if (v2_single_span(vsp, C)) {
+                        const uint32_t bytes = (uint32_t)((kV2TP - 1) * vsp + C) * 4u;
+                        v2_mbar_expect_tx(&bars.v_full[s], bytes);
+                        v2_bulk_load(dst, src, bytes, &bars.v_full[s]);
+                    } else {
+                        v2_mbar_expect_tx(&bars.v_full[s], (uint32_t)(kV2TP * C) * 4u);
+                        for (int r = 0; r < kV2TP; ++r)
+                            v2_bulk_load(dst + r * C, src + (int64_t)r * vsp, (uint32_t)C * 4u, &bars.v_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp <= 4) {
+        // ---------------- score warps: softmax of tile it, then the finish of tile it - 1 ----------------
+        const int lt = tid - 32;
+        const int pixel = lt >> 4, l = lt & 15;
+        const int gbase = (tid & 31) & ~(G - 1);
+        const unsigned gm = group_mask<G>();
+        const float scale = g.scale_ptr ? __ldg(g.scale_ptr) : 1.f;
+        const bool kcol = l < g.d4;
+        float a_prev[SPL], r_prev[SPL];
+        float dsc_local = 0.f;
+        int prev_pix = -1;
+
+        auto finish = [&](int pix, uint32_t itp) {
+            const int buf = itp & 1;
+            const int b = pix / g.P, p = pix - b * g.P;
+            v2_mbar_wait(&bars.da_full[buf], (itp >> 1) & 1);
+            float da[SPL], ds[SPL];
+            float dsum = 0.f;
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                const int j = l + u * G;
+                da[u] = (j < g.n) ? s_da[buf][pixel][j] : 0.f;
+                dsum += a_prev[u] * da[u];
+            }
+            v2_mbar_arrive(&bars.da_empty[buf]);
+            dsum = group_sum<G>(dsum, gm);
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                ds[u] = a_prev[u] * (da[u] - dsum);
+                dsc_local += ds[u] * r_prev[u];
+                const int j = l + u * G;
+                if (g.attn_out && j < g.n) {
+                    g.attn_out[(int64_t)pix * g.n + j] = a_prev[u];
+                    g.ds_out[(int64_t)pix * g.n + j] = ds[u] * scale;
+                }
+            }
+            const float* qp = q + (int64_t)pix * g.q_sp;
+            const float* ks = kstash + (size_t)(buf * kV2TP + pixel) * kst_pixel;
+            float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), dqv = qv;
+            if (kcol) qv = ld4(qp + 4 * l);
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                const int jend = min(g.n, (u + 1) * G);
+                for (int j0 = u * G; j0 < jend; j0 += 4) {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const int j = j0 + w;
+                        if (j >= jend) break;
+                        const float dsj = __shfl_sync(gm, ds[u], gbase + (j & (G - 1))) * scale;
+                        if (kcol) {
+                            fma4(dqv, dsj, *reinterpret_cast<const float4*>(ks + (j * g.d4 + l) * 4));
+                            float* dkp = tg.dk[j];
+                            if (dkp) {
+                                dkp += (int64_t)b * tg.k_sb[j] + (int64_t)p * tg.k_sp[j] + 4 * l;
+                                *reinterpret_cast<float4*>(dkp) =
+                                    make_float4(dsj * qv.x, dsj * qv.y, dsj * qv.z, dsj * qv.w);
+                            }
+                        }
+                    }
+                }
+            }
+            if (kcol && dq) *reinterpret_cast<float4*>(dq + (int64_t)pix * g.q_sp + 4 * l) = dqv;
+        };
+
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int pix = t * kV2TP + pixel;
+            const int b = pix / g.P, p = pix - b * g.P;
+            float a[SPL], r[SPL];
+            const int buf = it & 1;
+            // (the stash of tile it - 2 in this buffer was consumed by finish(it - 2) one iteration ago)
+            dw_scores<G, SPL>(tb, g, l, b, p, q + (int64_t)pix * g.q_sp, a, r, gm, scale,
+                              kstash + (size_t)(buf * kV2TP + pixel) * kst_pixel);
+            __syncwarp();
+            if (it >= 2) v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1);
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                const int j = l + u * G;
+                if (j < g.n) s_a[buf][pixel][j] = a[u];
+            }
+            v2_mbar_arrive(&bars.a_full[buf]);
+            if (it >= 1) finish(prev_pix, it - 1);
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) { a_prev[u] = a[u]; r_prev[u] = r[u]; }
+            prev_pix = pix;
+        }
+        if (it >= 1) finish(prev_pix, it - 1);
+        if (dscale) {
+            dsc_local = group_sum<32>(dsc_local);
+            if ((tid & 31) == 0) atomicAdd(dscale, dsc_local);
+        }
+    } else {
+        // ---------------- stream warps: da_j = <V_j, g>, dV_j = a_j g over the staged tiles ----------------
+        const int lt = tid - 160;
+        const int pixel = lt >> 4, l = lt & 15;
+        const unsigned gm = group_mask<G>();
+        const bool last_ok = (l + (ITERS - 1) * G) < g.C4;
+        const int orow = v2_single_span((int)g.o_sp, C) ? (int)g.o_sp : C;
+        uint32_t gc = 0, it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int pix = t * kV2TP + pixel;
+            const int b = pix / g.P, p = pix - b * g.P;
+            float4 go[ITERS];
+            {   // the dOut tile is the first ring entry of the tile
+                const int s = gc % kV2Stages;
+                v2_mbar_wait(&bars.v_full[s], (gc / kV2Stages) & 1);
+                const float* row = ring + (size_t)s * stage_floats + pixel * orow + 4 * l;
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i)
+                    go[i] = (i < ITERS - 1 || last_ok) ? *reinterpret_cast<const float4*>(row + 4 * i * G)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                if ((tid & 31) == 0) v2_mbar_arrive(&bars.v_empty[s]);
+                ++gc;
+            }
+            v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1);
+            if (it >= 2) v2_mbar_wait(&bars.da_empty[buf], ((it >> 1) - 1) & 1);
+            for (int j = 0; j < g.n; ++j, ++gc) {
+                const int s = gc % kV2Stages;
+                const int vsp = tb.v_sp[j];
+                const int rs = v2_single_span(vsp, C) ? vsp : C;
+                v2_mbar_wait(&bars.v_full[s], (gc / kV2Stages) & 1);
+                const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * l;
+                float part = 0.f;
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i)
+                    if (i < ITERS - 1 || last_ok) part += dot4(*reinterpret_cast<const float4*>(row + 4 * i * G), go[i]);
+                __syncwarp();
+                if ((tid & 31) == 0) v2_mbar_arrive(&bars.v_empty[s]);
+                part = group_sum<G>(part, gm);
+                if (l == 0) s_da[buf][pixel][j] = part;
+                float* dvp = tg.dv[j];
+                if (dvp) {
+                    const float aj = s_a[buf][pixel][j];
+                    dvp += (int64_t)b * tg.v_sb[j] + (int64_t)p * tg.v_sp[j] + 4 * l;
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i)
+                        if (i < ITERS - 1 || last_ok)
+                            st_stream4(dvp + 4 * i * G, make_float4(aj * go[i].x, aj * go[i].y, aj * go[i].z, aj * go[i].w));
+                }
+            }
+            v2_mbar_arrive(&bars.a_empty[buf]);
+            v2_mbar_arrive(&bars.da_full[buf]);
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // Gradient GATHER of the shared contexts (SURVEY.md 8f3, section 7 "backward bytes").  A context
@@ -785,6 +1037,29 @@ static int dw_bwd_impl(const char* fn, const SlotPtrs& sp, const SlotGradPtrs& g
         }
     }
     if (dscale) DAVI_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
+    // same crossover as the forward; the bulk-copy kernel has no read-modify-write (accumulate) variant
+    if (dw_v2_enabled() && g.acc_mask == 0 && g.C4 > 32 && g.C4 <= 80 && P % kV2TP == 0 && n >= 8 &&
+        (int64_t)n * g.total_pix >= 10 * 10240) {
+        int dev = 0, sms = 0;
+        DAVI_CUDA(cudaGetDevice(&dev));
+        DAVI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int ntiles = g.total_pix / kV2TP;
+        const int grid = ntiles < sms ? ntiles : sms;
+        const size_t smem = (size_t)kV2Stages * kV2TP * (C + kV2Slack) * sizeof(float) +
+                            (size_t)2 * kV2TP * n * d * sizeof(float);
+        if (smem <= 200 * 1024)
+        switch ((g.C4 + 15) / 16) {
+#define V2B_CASE(I)                                                                                        \
+    case I:                                                                                                \
+        DAVI_CUDA(cudaFuncSetAttribute(dw_attn_bwd_v2_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                        \
+        dw_attn_bwd_v2_kernel<I><<<grid, kV2Threads, smem, st>>>(sp, gp, q, dout, dq, dscale, g, ntiles);  \
+        break;
+            V2B_CASE(3) V2B_CASE(4) V2B_CASE(5) V2B_CASE(6) V2B_CASE(7) V2B_CASE(8)
+#undef V2B_CASE
+        }
+        if (smem <= 200 * 1024) return check_launch(fn);
+    }
     DW_DISPATCH(launch_bwd, sp, gp, q, dout, dq, dscale, g, st);
     return check_launch(fn);
 }

@@ -8,10 +8,64 @@
 //   bernoulli_nll : stat_tools/bernoulli.py:155-179
 //   is_logsumexp  : model/vae.py:480-482
 // The reference runs each as dozens of elementwise TF kernels; here each is one
-// launch.  One CTA per image reduces deterministically (fixed tree, no atomics).
+// launch over (pixel tile x image): the CTAs of one image form a THREAD-BLOCK CLUSTER, each
+// reduces its tile and rank 0 adds the partial sums of its peers out of their shared memory
+// (DSMEM) in rank order -- one launch, no workspace, no atomics, deterministic.
+#include <cooperative_groups.h>
+
 #include "davi_common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace davi {
+
+constexpr int kMaxTiles = 8;     // portable cluster size
+
+// Per-image totals of NV per-thread partial sums across the cluster of CTAs that share blockIdx.y.
+// `red` >= 32 floats, `part` NV floats, both shared.  Results are valid in thread 0 of rank 0.
+template <int NV>
+__device__ __forceinline__ void image_reduce(float (&v)[NV], float* red, float* part) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float t = block_sum(v[i], red);
+        if (threadIdx.x == 0) part[i] = t;
+    }
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    if (cl.block_rank() == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float t = part[i];
+            for (unsigned r = 1; r < cl.num_blocks(); ++r) t += *cl.map_shared_rank(part + i, r);
+            v[i] = t;
+        }
+    }
+    cl.sync();                   // peers keep their shared memory alive until rank 0 has read it
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_tiles(void (*kern)(KArgs...), int tiles, int B, int threads, cudaStream_t st,
+                                Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles, (unsigned)B);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)tiles;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+static int tiles_for(int64_t items, int per_cta) {
+    int64_t t = (items + per_cta - 1) / per_cta;
+    int r = 1;
+    while (r < kMaxTiles && r < t) r *= 2;
+    return r;
+}
 
 constexpr float kHalfLog2Pi = 0.9189385332046727f;
 
@@ -68,21 +122,29 @@ __device__ __forceinline__ GaussElem gauss_elem(float d_mu, float d_ls, bool has
     return e;
 }
 
-constexpr int kGaussThreads = 512;
+constexpr int kGaussThreads = 128;
 
+// grad (nullable) [B,P,6z]: with it the forward also emits, per element, everything the gradient needs so that
+// the backward sweep is one multiply-add pass without transcendentals (the KL's own upstream gradient is the
+// known scalar beta / B_global; it is applied in the backward so any upstream works):
+//   grad[row + 0z + c] = dKL / d mu_post_raw      grad[row + 1z + c] = dKL / d ls_post_raw
+//   grad[row + 2z + c] = dKL / d mu_prior_raw     grad[row + 3z + c] = dKL / d ls_prior_raw   (both paths: p and q)
+//   grad[row + 4z + c] = d xi / d mu_raw          grad[row + 5z + c] = d xi / d ls_raw         (sample path)
 __global__ void __launch_bounds__(kGaussThreads)
 gauss_kl_fwd_kernel(const float* __restrict__ post, const float* __restrict__ prior,
                     const float* __restrict__ eps, const float* __restrict__ noise_post,
                     const float* __restrict__ noise_prior, float* __restrict__ xi,
                     float* __restrict__ kl, float* __restrict__ logq, float* __restrict__ logp,
-                    int P, int z, Bound bq, Bound bp, float std_q, float std_p) {
+                    float* __restrict__ grad, int P, int z, Bound bq, Bound bp, float std_q, float std_p) {
     __shared__ float red[32];
-    const int b = blockIdx.x;
+    __shared__ float part[3];
+    const int b = blockIdx.y;
     const int64_t ne = (int64_t)P * z;
     const float* po = post + (int64_t)b * ne * 2;
     const float* pr = prior ? prior + (int64_t)b * ne * 2 : nullptr;
-    float akl = 0.f, aq = 0.f, ap = 0.f;
-    for (int64_t e = threadIdx.x; e < ne; e += kGaussThreads) {
+    float acc[3] = {0.f, 0.f, 0.f};                                      // kl, log q, log p
+    for (int64_t e = (int64_t)blockIdx.x * kGaussThreads + threadIdx.x; e < ne;
+         e += (int64_t)gridDim.x * kGaussThreads) {
         const int64_t p = e / z;
         const int c = (int)(e - p * z);
         const int64_t row = p * 2 * z;
@@ -101,20 +163,53 @@ gauss_kl_fwd_kernel(const float* __restrict__ post, const float* __restrict__ pr
         xi[ge] = x;
         const float lsq = logf(g.sq), lsp = logf(g.sp);
         const float dm = (g.loc_p - g.loc_q) / g.sp, rs = g.sq / g.sp;
-        akl += lsp - lsq + 0.5f * (rs * rs + dm * dm - 1.f);             // vl.py:540
+        acc[0] += lsp - lsq + 0.5f * (rs * rs + dm * dm - 1.f);          // vl.py:540
         if (logq) {
-            aq += -0.5f * ep * ep - lsq - kHalfLog2Pi;                   // vl.py:515
+            acc[1] += -0.5f * ep * ep - lsq - kHalfLog2Pi;               // vl.py:515
             const float zp = (x - g.loc_p) / g.sp;
-            ap += -0.5f * zp * zp - lsp - kHalfLog2Pi;                   // vl.py:526
+            acc[2] += -0.5f * zp * zp - lsp - kHalfLog2Pi;               // vl.py:526
+        }
+        if (grad) {
+            float* gr = grad + ((int64_t)b * P + p) * 6 * z;
+            const float isp2 = 1.f / (g.sp * g.sp);
+            const float diff = g.loc_q - g.loc_p;
+            const float kq_mu = diff * isp2 * g.dlocq_dmu;
+            const float kq_ls = (g.sq * isp2 - 1.f / g.sq) * g.dsq_dls;
+            gr[c] = kq_mu;
+            gr[z + c] = kq_ls;
+            gr[2 * z + c] = -diff * isp2 * g.dlocp_dmu + kq_mu;          // raw prior feeds p AND q (gd.py:214-221)
+            gr[3 * z + c] = (1.f / g.sp - (g.sq * g.sq + diff * diff) * isp2 / g.sp) * g.dsp_dls + kq_ls;
+            gr[4 * z + c] = g.dlocq_dmu;
+            gr[5 * z + c] = ep * g.dsq_dls;
         }
     }
-    akl = block_sum(akl, red);
-    if (threadIdx.x == 0) kl[b] = akl;
-    if (logq) {
-        aq = block_sum(aq, red);
-        if (threadIdx.x == 0) logq[b] = aq;
-        ap = block_sum(ap, red);
-        if (threadIdx.x == 0) logp[b] = ap;
+    image_reduce<3>(acc, red, part);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        kl[b] = acc[0];
+        if (logq) { logq[b] = acc[1]; logp[b] = acc[2]; }
+    }
+}
+
+// backward from the forward's saved `grad`: dpost = dkl[b] * dKL/dpost + dxi * dxi/dpost (same for the raw prior)
+__global__ void __launch_bounds__(256)
+gauss_kl_bwd_saved_kernel(const float* __restrict__ grad, const float* __restrict__ dxi,
+                          const float* __restrict__ dkl, float* __restrict__ dpost,
+                          float* __restrict__ dprior, int64_t total, int P, int z) {
+    const int64_t ge = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ge >= total) return;
+    const int64_t pix = ge / z;
+    const int c = (int)(ge - pix * z);
+    const int64_t b = pix / P;
+    const float* gr = grad + pix * 6 * z;
+    const float gx = dxi ? dxi[ge] : 0.f;
+    const float gk = dkl ? dkl[b] : 0.f;
+    const float sm = gx * gr[4 * z + c], sl = gx * gr[5 * z + c];
+    const int64_t row = pix * 2 * z;
+    dpost[row + c] = fmaf(gk, gr[c], sm);
+    dpost[row + z + c] = fmaf(gk, gr[z + c], sl);
+    if (dprior) {
+        dprior[row + c] = fmaf(gk, gr[2 * z + c], sm);
+        dprior[row + z + c] = fmaf(gk, gr[3 * z + c], sl);
     }
 }
 
@@ -165,7 +260,7 @@ gauss_kl_bwd_kernel(const float* __restrict__ post, const float* __restrict__ pr
 
 constexpr int kMix = 5;
 constexpr int kDlmCh = 10 * kMix;  // 5 logits + 5*(3 coeffs + 3 locs + 3 log-scales)
-constexpr int kDlmThreads = 256;
+constexpr int kDlmThreads = 128;
 
 // channel of loc[c][k] / log_scale[c][k] inside the 50-channel parameter row,
 // obtained by replaying the reshapes of dlm.py:175-184:
@@ -177,9 +272,10 @@ __global__ void __launch_bounds__(kDlmThreads)
 dlm_nll_kernel(const float* __restrict__ params, const float* __restrict__ x,
                float* __restrict__ nll, float* __restrict__ dparams, int P, float ls_low) {
     __shared__ float red[32];
-    const int b = blockIdx.x;
+    __shared__ float part[1];
+    const int b = blockIdx.y;
     float acc = 0.f;
-    for (int p = threadIdx.x; p < P; p += kDlmThreads) {
+    for (int p = blockIdx.x * kDlmThreads + threadIdx.x; p < P; p += gridDim.x * kDlmThreads) {
         const int64_t pix = (int64_t)b * P + p;
         float pr[kDlmCh];
         {
@@ -286,8 +382,9 @@ dlm_nll_kernel(const float* __restrict__ params, const float* __restrict__ x,
             for (int i = 0; i < kDlmCh / 2; ++i) gp[i] = make_float2(gr[2 * i], gr[2 * i + 1]);
         }
     }
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) nll[b] = acc;
+    float tot[1] = {acc};
+    image_reduce<1>(tot, red, part);
+    if (blockIdx.x == 0 && threadIdx.x == 0) nll[b] = tot[0];
 }
 
 // ---- Bernoulli ------------------------------------------------------------
@@ -296,10 +393,11 @@ __global__ void __launch_bounds__(256)
 bernoulli_nll_kernel(const float* __restrict__ logits, const float* __restrict__ x,
                      float* __restrict__ nll, float* __restrict__ dlogits, int H, int W, int crop) {
     __shared__ float red[32];
-    const int b = blockIdx.x;
+    __shared__ float part[1];
+    const int b = blockIdx.y;
     const int P = H * W;
     float acc = 0.f;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         const int h = p / W, w = p - h * W;
         const bool in = h >= crop && h < H - crop && w >= crop && w < W - crop;   // bern.py:177
         const int64_t i = (int64_t)b * P + p;
@@ -307,8 +405,9 @@ bernoulli_nll_kernel(const float* __restrict__ logits, const float* __restrict__
         if (in) acc += softplusf(l) - xv * l;                                     // -(x l - softplus(l))
         if (dlogits) dlogits[i] = in ? sigmoidf(l) - xv : 0.f;
     }
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) nll[b] = acc;
+    float tot[1] = {acc};
+    image_reduce<1>(tot, red, part);
+    if (blockIdx.x == 0 && threadIdx.x == 0) nll[b] = tot[0];
 }
 
 __global__ void scale_rows_kernel(const float* __restrict__ in, const float* __restrict__ w,
@@ -340,14 +439,27 @@ extern "C" int davi_gauss_kl_fwd(const float* post, const float* prior, const fl
                                  const float* noise_post, const float* noise_prior, float* xi,
                                  float* kl, float* logq, float* logp, int B, int P, int z,
                                  float post_lo, float post_hi, float prior_lo, float prior_hi,
-                                 float noise_std_post, float noise_std_prior, davi_stream_t stream) {
+                                 float noise_std_post, float noise_std_prior, float* grad,
+                                 davi_stream_t stream) {
     DAVI_REQUIRE(post && eps && xi && kl, "null pointer");
     DAVI_REQUIRE(B > 0 && P > 0 && z > 0, "shape");
     DAVI_REQUIRE((logq == nullptr) == (logp == nullptr), "logq and logp go together");
     DAVI_REQUIRE(post_hi > post_lo && prior_hi > prior_lo, "bounds");
-    gauss_kl_fwd_kernel<<<B, kGaussThreads, 0, (cudaStream_t)stream>>>(
-        post, prior, eps, noise_post, noise_prior, xi, kl, logq, logp, P, z,
-        make_bound(post_lo, post_hi), make_bound(prior_lo, prior_hi), noise_std_post, noise_std_prior);
+    const int tiles = tiles_for((int64_t)P * z, 4 * kGaussThreads);
+    DAVI_CUDA(launch_tiles(gauss_kl_fwd_kernel, tiles, B, kGaussThreads, (cudaStream_t)stream,
+                           post, prior, eps, noise_post, noise_prior, xi, kl, logq, logp, grad, P, z,
+                           make_bound(post_lo, post_hi), make_bound(prior_lo, prior_hi), noise_std_post,
+                           noise_std_prior));
+    return check_launch(__func__);
+}
+
+extern "C" int davi_gauss_kl_bwd_saved(const float* grad, const float* dxi, const float* dkl, float* dpost,
+                                       float* dprior, int B, int P, int z, davi_stream_t stream) {
+    DAVI_REQUIRE(grad && dpost, "null pointer");
+    DAVI_REQUIRE(B > 0 && P > 0 && z > 0, "shape");
+    const int64_t total = (int64_t)B * P * z;
+    gauss_kl_bwd_saved_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        grad, dxi, dkl, dpost, dprior, total, P, z);
     return check_launch(__func__);
 }
 
@@ -375,8 +487,8 @@ extern "C" int davi_dlm_nll_fwd(const float* params, const float* x, float* nll,
     DAVI_REQUIRE(B > 0 && P > 0, "shape");
     DAVI_REQUIRE((reinterpret_cast<uintptr_t>(params) & 7u) == 0 &&
                      (!dparams || (reinterpret_cast<uintptr_t>(dparams) & 7u) == 0), "alignment");
-    dlm_nll_kernel<<<B, kDlmThreads, 0, (cudaStream_t)stream>>>(params, x, nll, dparams, P,
-                                                                 log_scale_low_bound);
+    DAVI_CUDA(launch_tiles(dlm_nll_kernel, tiles_for(P, kDlmThreads), B, kDlmThreads, (cudaStream_t)stream,
+                           params, x, nll, dparams, P, log_scale_low_bound));
     return check_launch(__func__);
 }
 
@@ -385,7 +497,8 @@ extern "C" int davi_bernoulli_nll_fwd(const float* logits, const float* x, float
                                       davi_stream_t stream) {
     DAVI_REQUIRE(logits && x && nll, "null pointer");
     DAVI_REQUIRE(B > 0 && H > 0 && W > 0 && crop >= 0 && 2 * crop < H && 2 * crop < W, "shape");
-    bernoulli_nll_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, x, nll, dlogits, H, W, crop);
+    DAVI_CUDA(launch_tiles(bernoulli_nll_kernel, tiles_for((int64_t)H * W, 256), B, 256, (cudaStream_t)stream,
+                           logits, x, nll, dlogits, H, W, crop));
     return check_launch(__func__);
 }
 

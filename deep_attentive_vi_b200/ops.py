@@ -529,6 +529,9 @@ def nonlocal_attn_packed(qkv, x, d, scale, gamma):
 # ---------------------------------------------------------------------------
 
 class _GaussKl(torch.autograd.Function):
+    """The forward launch also emits the gradient (davi_gauss_kl_fwd `grad`): the backward is one
+    multiply-add pass over it (davi_gauss_kl_bwd_saved)."""
+
     @staticmethod
     def forward(ctx, post, prior, eps, noise_post, noise_prior, cfg):
         _require_cuda(post, prior, eps, noise_post, noise_prior)
@@ -545,11 +548,13 @@ class _GaussKl(torch.autograd.Function):
         kl = torch.empty(B, device=post.device, dtype=torch.float32)
         logq = torch.empty_like(kl) if want_logp else None
         logp = torch.empty_like(kl) if want_logp else None
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        grad = torch.empty((B, P, 6 * z), device=post.device, dtype=torch.float32) if need else None
         _lib_call("davi_gauss_kl_fwd", _p(post), _p(prior), _p(eps), _p(noise_post), _p(noise_prior),
                   _p(xi), _p(kl), _p(logq), _p(logp), B, P, z, post_lo, post_hi, prior_lo, prior_hi,
-                  std_q, std_p, _stream())
-        ctx.save_for_backward(post, prior, eps, noise_post, noise_prior)
-        ctx.cfg = (B, P, z) + tuple(cfg[:6])
+                  std_q, std_p, _p(grad), _stream())
+        ctx.save_for_backward(grad)
+        ctx.cfg = (B, P, z, prior is not None, post.shape)
         if want_logp:
             ctx.mark_non_differentiable(logq, logp)
             return xi, kl, logq, logp
@@ -557,15 +562,13 @@ class _GaussKl(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dxi, dkl, *unused):
-        post, prior, eps, noise_post, noise_prior = ctx.saved_tensors
-        B, P, z, post_lo, post_hi, prior_lo, prior_hi, std_q, std_p = ctx.cfg
+        (grad,) = ctx.saved_tensors
+        B, P, z, has_prior, shape = ctx.cfg
         dxi = dxi.contiguous() if dxi is not None else None
         dkl = dkl.contiguous() if dkl is not None else None
-        dpost = torch.empty_like(post)
-        dprior = torch.empty_like(prior) if prior is not None else None
-        _lib_call("davi_gauss_kl_bwd", _p(post), _p(prior), _p(eps), _p(noise_post), _p(noise_prior),
-                  _p(dxi), _p(dkl), _p(dpost), _p(dprior), B, P, z, post_lo, post_hi, prior_lo,
-                  prior_hi, std_q, std_p, _stream())
+        dpost = torch.empty(shape, device=grad.device, dtype=torch.float32)
+        dprior = torch.empty_like(dpost) if has_prior else None
+        _lib_call("davi_gauss_kl_bwd_saved", _p(grad), _p(dxi), _p(dkl), _p(dpost), _p(dprior), B, P, z, _stream())
         return dpost, dprior, None, None, None, None
 
 

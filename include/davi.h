@@ -240,6 +240,14 @@ int davi_nonlocal_attn_bwd(const float* Q, const float* K, const float* V,
  *   kl [B]; logq, logp (nullable) [B]
  *   bounds: loc = 5 tanh(mu/10); sigma = exp(bound(ls, lo, hi)) + 1e-2 with
  *         tanh form when |lo| == |hi| else smoothstep (gd.py:175-185).
+ *   grad  (nullable) [B,P,6z]: the fused forward+backward form (north_star (3)).  The KL's own
+ *         upstream gradient is the known scalar beta / B_global, so the
+ *         forward pass emits the whole gradient in the same sweep, per pixel row:
+ *         [dKL/dmu_post | dKL/dls_post | dKL/dmu_prior | dKL/dls_prior | dxi/dmu | dxi/dls]
+ *         (the prior entries include the residual path through q); davi_gauss_kl_bwd_saved then
+ *         needs one multiply-add pass and no transcendental.
+ * One launch over (pixel tile x image); the tiles of an image are a thread-block cluster whose
+ * partial sums are combined through distributed shared memory (deterministic, no workspace).
  * ---------------------------------------------------------------------- */
 int davi_gauss_kl_fwd(const float* post, const float* prior, const float* eps,
                       const float* noise_post, const float* noise_prior,
@@ -247,10 +255,15 @@ int davi_gauss_kl_fwd(const float* post, const float* prior, const float* eps,
                       int B, int P, int z,
                       float post_lo, float post_hi, float prior_lo, float prior_hi,
                       float noise_std_post, float noise_std_prior,
-                      davi_stream_t stream);
+                      float* grad, davi_stream_t stream);
 
-/* Gradient: dxi [B,P,z] (nullable = 0) and dkl [B] (nullable = 0) ->
- * dpost [B,P,2z], dprior [B,P,2z] (NULL iff prior is NULL).  The raw prior
+/* Gradient from the forward's `grad`: dpost = dkl[b] * dKL/dpost + dxi * dxi/dpost, likewise for
+ * the raw prior (dprior NULL for layer 0).  dxi [B,P,z] / dkl [B] nullable = 0. */
+int davi_gauss_kl_bwd_saved(const float* grad, const float* dxi, const float* dkl,
+                            float* dpost, float* dprior, int B, int P, int z, davi_stream_t stream);
+
+/* Gradient by recomputation (no `grad` saved): dxi [B,P,z] (nullable = 0) and dkl [B]
+ * (nullable = 0) -> dpost [B,P,2z], dprior [B,P,2z] (NULL iff prior is NULL).  The raw prior
  * parameters receive gradient through BOTH p and the residual q. */
 int davi_gauss_kl_bwd(const float* post, const float* prior, const float* eps,
                       const float* noise_post, const float* noise_prior,

@@ -268,10 +268,15 @@ def test_dw_attn_headline_shapes_match_oracle_on_the_bulk_copy_kernel(cuda, n, C
     assert rel_err(vg.grad, vr.grad) < 1e-5
     _lib.set_option(_lib.OPT_DW_IMPL, 1)
     try:
-        out_v1 = ops.dw_attn(qg.detach(), kg.detach(), vg.detach(), sc.to(cuda))
+        q1, k1, v1 = (t.to(cuda).requires_grad_() for t in (q, k, v))
+        out_v1 = ops.dw_attn(q1, k1, v1, sc.to(cuda))
+        out_v1.backward(go.to(cuda))
     finally:
         _lib.set_option(_lib.OPT_DW_IMPL, 0)
-    assert torch.equal(out.detach(), out_v1), (out.detach() - out_v1).abs().max().item()
+    assert torch.equal(out.detach(), out_v1.detach()), (out.detach() - out_v1.detach()).abs().max().item()
+    # the persistent bulk-copy BACKWARD (dw_attn_bwd_v2_kernel) against the register-streaming one
+    for a, b in ((qg, q1), (kg, k1), (vg, v1)):
+        assert rel_err(a.grad, b.grad) < 1e-6
 
 
 def test_nonlocal_forced_exact_kernels_match_tensor_core_kernels(cuda):
@@ -534,3 +539,34 @@ def test_dw_attn_backward_saves_weights_for_the_gather(cuda):
         else:
             assert rel_err(dvj[j], a[..., j:j + 1] * gd) < 1e-5
             assert rel_err(dkj[j], 0.8 * ds[..., j:j + 1] * qd) < 1e-5
+
+
+@pytest.mark.parametrize("B,P,z,has_prior", [(3, 256, 20, True), (2, 4, 4, True), (5, 100, 12, False)])
+def test_gauss_kl_saved_gradient_equals_recomputed_gradient(cuda, B, P, z, has_prior):
+    """The gradient the forward launch emits (`grad`, consumed by davi_gauss_kl_bwd_saved) against the
+    recomputing backward davi_gauss_kl_bwd on the same inputs; tile counts 1 (single-CTA cluster) .. 8."""
+    from deep_attentive_vi_b200 import _lib
+    torch.manual_seed(B + P)
+    post = torch.randn(B, P, 2 * z, device=cuda) * 2
+    prior = torch.randn(B, P, 2 * z, device=cuda) * 3 if has_prior else None
+    eps, n1 = torch.randn(B, P, z, device=cuda), torch.randn(B, P, z, device=cuda)
+    n2 = torch.randn(B, P, z, device=cuda) if has_prior else None
+    dxi, dkl = torch.randn(B, P, z, device=cuda), torch.randn(B, device=cuda)
+    xi, kl = torch.empty(B, P, z, device=cuda), torch.empty(B, device=cuda)
+    grad = torch.empty(B, P, 6 * z, device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: 0 if t is None else t.data_ptr()
+    cfg = (-5.0, 5.0, -1.0, 5.0, 0.3, 0.2)
+    _lib.call("davi_gauss_kl_fwd", p(post), p(prior), p(eps), p(n1), p(n2), p(xi), p(kl), 0, 0, B, P, z, *cfg,
+              p(grad), st)
+    xi0, kl0 = torch.empty_like(xi), torch.empty_like(kl)
+    _lib.call("davi_gauss_kl_fwd", p(post), p(prior), p(eps), p(n1), p(n2), p(xi0), p(kl0), 0, 0, B, P, z, *cfg, 0, st)
+    assert torch.equal(xi, xi0) and torch.equal(kl, kl0)
+    a, b = torch.empty_like(post), (torch.empty_like(post) if has_prior else None)
+    _lib.call("davi_gauss_kl_bwd_saved", p(grad), p(dxi), p(dkl), p(a), p(b), B, P, z, st)
+    a2, b2 = torch.empty_like(post), (torch.empty_like(post) if has_prior else None)
+    _lib.call("davi_gauss_kl_bwd", p(post), p(prior), p(eps), p(n1), p(n2), p(dxi), p(dkl), p(a2), p(b2), B, P, z,
+              *cfg, st)
+    assert rel_err(a, a2) < 2e-6
+    if has_prior:
+        assert rel_err(b, b2) < 2e-6

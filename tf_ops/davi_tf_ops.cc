@@ -229,7 +229,7 @@ class DaviGaussKlOp : public OpKernel {
     OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({B}), &lp));
     OP_REQUIRES_OK(ctx, Check(davi_gauss_kl_fwd(P(post), has_prior_ ? P(prior) : nullptr, P(eps), nullptr,
                                                 nullptr, P(xi), P(kl), P(lq), P(lp), B, Pn, z, qlo_, qhi_,
-                                                plo_, phi_, 0.f, 0.f, StreamOf(ctx)),
+                                                plo_, phi_, 0.f, 0.f, /*grad=*/nullptr, StreamOf(ctx)),
                               "davi_gauss_kl_fwd"));
   }
  private:
