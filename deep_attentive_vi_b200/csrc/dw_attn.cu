@@ -23,6 +23,41 @@
 
 namespace davi {
 
+// Optional phase trace for profiling sessions (tools/dw_trace.py builds a SECOND library with -DDAVI_DW_TRACE; the
+// product build compiles none of it): clock64 stamps of the first and the last CTA of a persistent launch.
+#ifdef DAVI_DW_TRACE
+__device__ long long g_dw_trace[2][64];
+#define DW_STAMP(i)                                                                          \
+    do {                                                                                     \
+        if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) g_dw_trace[blockIdx.x != 0][i] = clock64(); \
+    } while (0)
+// DW_WAIT(i, stmt): runs stmt and adds its duration to trace slot i (a role's time blocked on a barrier)
+#define DW_WAIT(i, stmt)                                                                      \
+    do {                                                                                      \
+        const long long t0_ = clock64();                                                      \
+        stmt;                                                                                 \
+        if ((threadIdx.x & 31) == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))      \
+            g_dw_trace[blockIdx.x != 0][i] += clock64() - t0_;                                \
+    } while (0)
+#define DW_TRACE_CLEAR()                                                                      \
+    do {                                                                                      \
+        if (threadIdx.x < 64 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))             \
+            g_dw_trace[blockIdx.x != 0][threadIdx.x] = 0;                                     \
+        __syncthreads();                                                                      \
+    } while (0)
+#else
+#define DW_STAMP(i) \
+    do {            \
+    } while (0)
+#define DW_WAIT(i, stmt) \
+    do {                 \
+        stmt;            \
+    } while (0)
+#define DW_TRACE_CLEAR() \
+    do {                 \
+    } while (0)
+#endif
+
 // every slot carries its own (batch, pixel) strides: a slot may be a channel slice of a wider
 // per-layer tensor, a dense fresh tensor, or layer j of a stacked tensor
 struct SlotPtrs {
@@ -74,10 +109,19 @@ __device__ __forceinline__ void dw_scores(const SlotTable& tb, const DwGeom& g, 
             const float* kp = tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j];
             float dot = 0.f;
             if (k_stash) {      // keep this pixel's key rows on chip for the dq / dK phase: [slot][d]
-                for (int c = 0; c < g.d4; ++c) {
-                    const float4 kv = ld4(kp + 4 * c);
-                    *reinterpret_cast<float4*>(k_stash + (j * g.d4 + c) * 4) = kv;
-                    dot += dot4(kv, ld4(qp + 4 * c));
+                // all loads of a batch are issued before the first shared-memory store (the compiler cannot
+                // move a generic load above a generic store: one DRAM round trip per float4 otherwise)
+                for (int c0 = 0; c0 < g.d4; c0 += 8) {
+                    float4 kv[8], qv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c0 + c < g.d4) { kv[c] = ld4(kp + 4 * (c0 + c)); qv[c] = ld4(qp + 4 * (c0 + c)); }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c0 + c < g.d4) {
+                            *reinterpret_cast<float4*>(k_stash + (j * g.d4 + c0 + c) * 4) = kv[c];
+                            dot += dot4(kv[c], qv[c]);
+                        }
                 }
             } else
             for (int c = 0; c < g.d4; ++c) dot += dot4(ld4(kp + 4 * c), ld4(qp + 4 * c));
@@ -252,6 +296,10 @@ __device__ __forceinline__ void v2_bulk_load(void* smem_dst, const void* gsrc, u
         : "memory");
 }
 
+__device__ __forceinline__ void v2_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(v2_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 // per-slot staging plan: a tile of slot j is either one contiguous span (row stride kept) or,
 // when the slot's rows are far apart, kV2TP row copies packed densely
 __device__ __forceinline__ bool v2_single_span(int v_sp, int C) { return v_sp - C <= kV2Slack; }
@@ -276,22 +324,20 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
         tb.k_sb[j] = sp.k_sb[j]; tb.k_sp[j] = sp.k_sp[j];
         tb.v_sb[j] = sp.v_sb[j]; tb.v_sp[j] = sp.v_sp[j];
     }
-    if (tid == 0) {
-        for (int s = 0; s < kV2Stages; ++s) { v2_mbar_init(&bars.v_full[s], 1); v2_mbar_init(&bars.v_empty[s], 4); }
-        for (int i = 0; i < 2; ++i) { v2_mbar_init(&bars.a_full[i], 128); v2_mbar_init(&bars.a_empty[i], 128); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    // barrier init spread over the producer warp's lanes (one thread doing all 36 took ~1 us of every launch)
+    if (tid >= 32 && tid < 32 + kV2Stages) { v2_mbar_init(&bars.v_full[tid - 32], 1); v2_mbar_init(&bars.v_empty[tid - 32], 4); }
+    if (tid >= 64 && tid < 66) { v2_mbar_init(&bars.a_full[tid - 64], 128); v2_mbar_init(&bars.a_empty[tid - 64], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     if (warp == 0) {
-        // ---------------- producer warp: lane s issues every bulk copy into ring stage s ----------------
-        {
+        // ---------------- producer: one thread issues every bulk copy ----------------
+        if (tid == 0) {
             uint32_t gc = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const int pix0 = t * kV2TP;
                 const int b = pix0 / g.P, p0 = pix0 - b * g.P;
                 for (int j = 0; j < g.n; ++j, ++gc) {
-                    if ((gc % kV2Stages) != (uint32_t)tid) continue;   // one lane per ring stage: its uses stay ordered
                     const int s = gc % kV2Stages;
                     if (gc >= kV2Stages) v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1);
                     const int vsp = tb.v_sp[j];
@@ -345,18 +391,37 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
             float4 acc[ITERS];
 #pragma unroll
             for (int i = 0; i < ITERS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = 0; j < g.n; ++j, ++gc) {
-                const int s = gc % kV2Stages;
-                const int vsp = tb.v_sp[j];
-                const int rs = v2_single_span(vsp, C) ? vsp : C;
-                const float aj = s_a[buf][pixel][j];
-                v2_mbar_wait(&bars.v_full[s], (gc / kV2Stages) & 1);
-                const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * l;
+            for (int j0 = 0; j0 < g.n; j0 += 2) {      // two staged tiles per round: their waits and loads overlap
+                float4 v[2][ITERS];
+                float aj[2];
 #pragma unroll
-                for (int i = 0; i < ITERS; ++i)
-                    if (i < ITERS - 1 || last_ok) fma4(acc[i], aj, *reinterpret_cast<const float4*>(row + 4 * i * G));
-                __syncwarp();                                  // one arrival per warp: all lanes have read the stage
-                if ((tid & 31) == 0) v2_mbar_arrive(&bars.v_empty[s]);
+                for (int u = 0; u < 2; ++u) {
+                    const int j = j0 + u;
+                    aj[u] = 0.f;
+                    if (j < g.n) {
+                        const uint32_t c = gc + u;
+                        const int s = c % kV2Stages;
+                        const int vsp = tb.v_sp[j];
+                        const int rs = v2_single_span(vsp, C) ? vsp : C;
+                        aj[u] = s_a[buf][pixel][j];
+                        v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1);
+                        const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * l;
+#pragma unroll
+                        for (int i = 0; i < ITERS; ++i)
+                            v[u][i] = (i < ITERS - 1 || last_ok) ? *reinterpret_cast<const float4*>(row + 4 * i * G)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        __syncwarp();                              // one arrival per warp: all lanes have read the stage
+                        if ((tid & 31) == 0) v2_mbar_arrive(&bars.v_empty[s]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < ITERS; ++i) v[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i) fma4(acc[i], aj[u], v[u][i]);
+                gc += min(2, g.n - j0);
             }
             v2_mbar_arrive(&bars.a_empty[buf]);
             float* op = out + (int64_t)(t * kV2TP + pixel) * g.o_sp + 4 * l;
@@ -574,7 +639,7 @@ dw_attn_bwd_small_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* 
 // ---------------------------------------------------------------------------------------
 struct V2BwdBars {
     uint64_t v_full[kV2Stages], v_empty[kV2Stages];
-    uint64_t a_full[2], a_empty[2], da_full[2], da_empty[2];
+    uint64_t a_full[2], a_empty[2], da_full[2], da_empty[2], go_full[2], go_empty[2];
 };
 
 template <int ITERS>
@@ -592,11 +657,15 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
     const int C = g.C4 * 4;
     const int stage_floats = kV2TP * (C + kV2Slack);
     float* ring = reinterpret_cast<float*>(v2_smem);
-    // key rows of the two tiles in flight: [2][kV2TP][n][d], written by the softmax phase, read by the finish phase
-    const int kst_pixel = g.n * g.d4 * 4;
-    float* kstash = ring + (size_t)kV2Stages * stage_floats;
+    // key and query rows of three tiles, [3][kV2TP][n + 1][d] (row n = the query): filled by cp.async one tile ahead
+    // of the softmax phase, read by the softmax phase and again by the finish phase one tile later
+    const int kst_pixel = (g.n + 1) * g.d4 * 4;
+    float* gbuf = ring + (size_t)kV2Stages * stage_floats;      // dOut tiles of the two tiles in flight
+    float* kstash = gbuf + (size_t)2 * stage_floats;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    DW_TRACE_CLEAR();
+    if (tid == 0) DW_STAMP(0);                                  // entry
     if (tid < DAVI_MAX_SLOTS) {
         const int j = tid;
         tb.k[j] = sp.k[j]; tb.v[j] = sp.v[j];
@@ -606,43 +675,45 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
         tg.k_sb[j] = gp.k_sb[j]; tg.k_sp[j] = gp.k_sp[j];
         tg.v_sb[j] = gp.v_sb[j]; tg.v_sp[j] = gp.v_sp[j];
     }
-    if (tid == 0) {
-        for (int s = 0; s < kV2Stages; ++s) { v2_mbar_init(&bars.v_full[s], 1); v2_mbar_init(&bars.v_empty[s], 4); }
-        for (int i = 0; i < 2; ++i) {
-            v2_mbar_init(&bars.a_full[i], 128); v2_mbar_init(&bars.a_empty[i], 128);
-            v2_mbar_init(&bars.da_full[i], 128); v2_mbar_init(&bars.da_empty[i], 128);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (tid >= 32 && tid < 32 + kV2Stages) { v2_mbar_init(&bars.v_full[tid - 32], 1); v2_mbar_init(&bars.v_empty[tid - 32], 1); }
+    if (tid >= 64 && tid < 66) {
+        const int i = tid - 64;
+        v2_mbar_init(&bars.a_full[i], 128); v2_mbar_init(&bars.a_empty[i], 128);
+        v2_mbar_init(&bars.da_full[i], 128); v2_mbar_init(&bars.da_empty[i], 128);
+        v2_mbar_init(&bars.go_full[i], 1); v2_mbar_init(&bars.go_empty[i], 4);
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    if (tid == 0) DW_STAMP(1);                                  // barriers + tables ready
 
     if (warp == 0) {
-        // ---------------- producer warp: per tile the dOut tile, then the n value tiles; lane s issues
-        // every bulk copy into ring stage s ----------------
-        {
-            uint32_t gc = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // ---------------- producer: per tile the dOut tile, then the n value tiles ----------------
+        if (tid == 0) {
+            uint32_t gc = 0, it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
                 const int pix0 = t * kV2TP;
                 const int b = pix0 / g.P, p0 = pix0 - b * g.P;
-                for (int j = -1; j < g.n; ++j, ++gc) {
-                    if ((gc % kV2Stages) != (uint32_t)tid) continue;   // one lane per ring stage: its uses stay ordered
-                    const int s = gc % kV2Stages;
-                    if (gc >= kV2Stages) v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1);
-                    float* dst = ring + (size_t)s * stage_floats;
-                    if (j < 0) {                          // dOut rows: dense stride o_sp
-                        const int osp = (int)g.o_sp;
-                        const float* src = dout + (int64_t)pix0 * osp;
-                        if (v2_single_span(osp, C)) {
-                            const uint32_t bytes = (uint32_t)((kV2TP - 1) * osp + C) * 4u;
-                            v2_mbar_expect_tx(&bars.v_full[s], bytes);
-                            v2_bulk_load(dst, src, bytes, &bars.v_full[s]);
-                        } else {
-                            v2_mbar_expect_tx(&bars.v_full[s], (uint32_t)(kV2TP * C) * 4u);
-                            for (int r = 0; r < kV2TP; ++r)
-                                v2_bulk_load(dst + r * C, src + (int64_t)r * osp, (uint32_t)C * 4u, &bars.v_full[s]);
-                        }
-                        continue;
+                {   // dOut rows (dense stride o_sp) -> the tile's own buffer
+                    const int gb = it & 1;
+                    if (it >= 2) v2_mbar_wait(&bars.go_empty[gb], ((it >> 1) - 1) & 1);
+                    const int osp = (int)g.o_sp;
+                    const float* src = dout + (int64_t)pix0 * osp;
+                    float* dst = gbuf + (size_t)gb * stage_floats;
+                    if (v2_single_span(osp, C)) {
+                        const uint32_t bytes = (uint32_t)((kV2TP - 1) * osp + C) * 4u;
+                        v2_mbar_expect_tx(&bars.go_full[gb], bytes);
+                        v2_bulk_load(dst, src, bytes, &bars.go_full[gb]);
+                    } else {
+                        v2_mbar_expect_tx(&bars.go_full[gb], (uint32_t)(kV2TP * C) * 4u);
+                        for (int r = 0; r < kV2TP; ++r)
+                            v2_bulk_load(dst + r * C, src + (int64_t)r * osp, (uint32_t)C * 4u, &bars.go_full[gb]);
                     }
+                }
+                for (int j = 0; j < g.n; ++j, ++gc) {
+                    const int s = gc % kV2Stages;
+                    if (gc == kV2Stages) DW_STAMP(2);           // producer: ring filled once
+                    if (gc >= kV2Stages) DW_WAIT(4, v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1));
+                    float* dst = ring + (size_t)s * stage_floats;
                     const int vsp = tb.v_sp[j];
                     const float* src = tb.v[j] + (int64_t)b * tb.v_sb[j] + (int64_t)p0 * vsp;
                     if (v2_single_span(vsp, C)) {
@@ -656,6 +727,7 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
                     }
                 }
             }
+            DW_STAMP(3);                                        // producer: everything issued
         }
     } else if (warp <= 4) {
         // ---------------- score warps: softmax of tile it, then the finish of tile it - 1 ----------------
@@ -669,10 +741,29 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
         float dsc_local = 0.f;
         int prev_pix = -1;
 
+        auto stash = [&](uint32_t itx) { return kstash + (size_t)((itx % 3) * kV2TP + pixel) * kst_pixel; };
+        // cp.async of this lane's key rows (slots l, l + 16) and of float4 column l of the query row of tile t
+        auto prefetch = [&](int t, uint32_t itx) {
+            const int pix = t * kV2TP + pixel;
+            const int b = pix / g.P, p = pix - b * g.P;
+            float* st = stash(itx);
+#pragma unroll
+            for (int u = 0; u < SPL; ++u) {
+                const int j = l + u * G;
+                if (j < g.n) {
+                    const float* kp = tb.k[j] + (int64_t)b * tb.k_sb[j] + (int64_t)p * tb.k_sp[j];
+                    for (int c = 0; c < g.d4; ++c) v2_cp_async16(st + (j * g.d4 + c) * 4, kp + 4 * c);
+                }
+            }
+            for (int c = l; c < g.d4; c += G) v2_cp_async16(st + (g.n * g.d4 + c) * 4, q + (int64_t)pix * g.q_sp + 4 * c);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+
         auto finish = [&](int pix, uint32_t itp) {
             const int buf = itp & 1;
             const int b = pix / g.P, p = pix - b * g.P;
-            v2_mbar_wait(&bars.da_full[buf], (itp >> 1) & 1);
+            if (lt == 0) DW_WAIT(5, v2_mbar_wait(&bars.da_full[buf], (itp >> 1) & 1));
+            else v2_mbar_wait(&bars.da_full[buf], (itp >> 1) & 1);
             float da[SPL], ds[SPL];
             float dsum = 0.f;
 #pragma unroll
@@ -693,10 +784,9 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
                     g.ds_out[(int64_t)pix * g.n + j] = ds[u] * scale;
                 }
             }
-            const float* qp = q + (int64_t)pix * g.q_sp;
-            const float* ks = kstash + (size_t)(buf * kV2TP + pixel) * kst_pixel;
+            const float* ks = stash(itp);
             float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), dqv = qv;
-            if (kcol) qv = ld4(qp + 4 * l);
+            if (kcol) qv = *reinterpret_cast<const float4*>(ks + (g.n * g.d4 + l) * 4);
 #pragma unroll
             for (int u = 0; u < SPL; ++u) {
                 const int jend = min(g.n, (u + 1) * G);
@@ -722,85 +812,147 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
         };
 
         uint32_t it = 0;
+        if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int pix = t * kV2TP + pixel;
-            const int b = pix / g.P, p = pix - b * g.P;
             float a[SPL], r[SPL];
             const int buf = it & 1;
-            // (the stash of tile it - 2 in this buffer was consumed by finish(it - 2) one iteration ago)
-            dw_scores<G, SPL>(tb, g, l, b, p, q + (int64_t)pix * g.q_sp, a, r, gm, scale,
-                              kstash + (size_t)(buf * kV2TP + pixel) * kst_pixel);
+            // the stash buffer of tile it + 1 was last read by finish(it - 2), one iteration ago
             __syncwarp();
-            if (it >= 2) v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1);
+            if (t + (int)gridDim.x < ntiles) {
+                prefetch(t + gridDim.x, it + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();                                       // the pixel's 16 lanes share one warp
+            {   // softmax over the staged key rows: lane l owns slots l, l + 16
+                const float* st = stash(it);
+                const float* qs = st + g.n * g.d4 * 4;
+                float sc[SPL];
+                float m = -INFINITY;
+#pragma unroll
+                for (int u = 0; u < SPL; ++u) {
+                    const int j = l + u * G;
+                    sc[u] = -INFINITY;
+                    r[u] = 0.f;
+                    if (j < g.n) {
+                        float dot = 0.f;
+                        for (int c = 0; c < g.d4; ++c)
+                            dot += dot4(*reinterpret_cast<const float4*>(st + (j * g.d4 + c) * 4),
+                                        *reinterpret_cast<const float4*>(qs + 4 * c));
+                        r[u] = dot;
+                        sc[u] = dot * scale;
+                    }
+                    m = fmaxf(m, sc[u]);
+                }
+                m = group_max<G>(m, gm);
+                float sum = 0.f;
+#pragma unroll
+                for (int u = 0; u < SPL; ++u) {
+                    a[u] = (l + u * G < g.n) ? __expf(sc[u] - m) : 0.f;
+                    sum += a[u];
+                }
+                sum = group_sum<G>(sum, gm);
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int u = 0; u < SPL; ++u) a[u] *= inv;
+            }
+            if (it >= 2) {
+                if (lt == 0) DW_WAIT(6, v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1));
+                else v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1);
+            }
 #pragma unroll
             for (int u = 0; u < SPL; ++u) {
                 const int j = l + u * G;
                 if (j < g.n) s_a[buf][pixel][j] = a[u];
             }
             v2_mbar_arrive(&bars.a_full[buf]);
+            if (lt == 0 && it < 12) DW_STAMP(8 + it);           // score: weights of tile it published
             if (it >= 1) finish(prev_pix, it - 1);
+            if (lt == 0 && it >= 1 && it < 13) DW_STAMP(20 + it - 1);   // score: tile it - 1 finished (dq, dK written)
 #pragma unroll
             for (int u = 0; u < SPL; ++u) { a_prev[u] = a[u]; r_prev[u] = r[u]; }
             prev_pix = pix;
         }
         if (it >= 1) finish(prev_pix, it - 1);
+        if (lt == 0) DW_STAMP(33);                              // score: last tile finished
         if (dscale) {
             dsc_local = group_sum<32>(dsc_local);
             if ((tid & 31) == 0) atomicAdd(dscale, dsc_local);
         }
     } else {
         // ---------------- stream warps: da_j = <V_j, g>, dV_j = a_j g over the staged tiles ----------------
+        // ONE warp owns a whole staged tile (slot j of the tile goes to warp j % 4), so four tiles are consumed
+        // concurrently and the per-stage overhead (wait, release, reduction, addressing: ~130 instructions of a
+        // lone warp, which bound the first version at ~700 cycles / stage) is paid once per 9 KB instead of four
+        // times.  Lane = (pixel, quarter): a lane covers float4 columns quarter, quarter + 4, ... of its pixel's
+        // row, the dot product is finished by two shuffles.
         const int lt = tid - 160;
-        const int pixel = lt >> 4, l = lt & 15;
-        const unsigned gm = group_mask<G>();
-        const bool last_ok = (l + (ITERS - 1) * G) < g.C4;
+        const int w = lt >> 5, lane = lt & 31;
+        const int pixel = lane >> 2, qd = lane & 3;
+        constexpr int NC = 4 * ITERS;                           // float4 columns per lane (C4 <= 16 ITERS)
         const int orow = v2_single_span((int)g.o_sp, C) ? (int)g.o_sp : C;
-        uint32_t gc = 0, it = 0;
+        uint32_t gc0 = 0, it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int buf = it & 1;
             const int pix = t * kV2TP + pixel;
             const int b = pix / g.P, p = pix - b * g.P;
-            float4 go[ITERS];
-            {   // the dOut tile is the first ring entry of the tile
-                const int s = gc % kV2Stages;
-                v2_mbar_wait(&bars.v_full[s], (gc / kV2Stages) & 1);
-                const float* row = ring + (size_t)s * stage_floats + pixel * orow + 4 * l;
+            float4 go[NC];
+            {
+                if (lt == 0) DW_WAIT(60, v2_mbar_wait(&bars.go_full[buf], (it >> 1) & 1));
+                else v2_mbar_wait(&bars.go_full[buf], (it >> 1) & 1);
+                const float* row = gbuf + (size_t)buf * stage_floats + pixel * orow + 4 * qd;
 #pragma unroll
-                for (int i = 0; i < ITERS; ++i)
-                    go[i] = (i < ITERS - 1 || last_ok) ? *reinterpret_cast<const float4*>(row + 4 * i * G)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < NC; ++i)
+                    go[i] = (qd + 4 * i < g.C4) ? *reinterpret_cast<const float4*>(row + 16 * i)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncwarp();
-                if ((tid & 31) == 0) v2_mbar_arrive(&bars.v_empty[s]);
-                ++gc;
+                if (lane == 0) v2_mbar_arrive(&bars.go_empty[buf]);
             }
-            v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1);
+            if (lt == 0 && it < 12) DW_STAMP(36 + it);          // stream: dOut tile of tile it received
+            if (lt == 0) DW_WAIT(61, v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1));
+            else v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1);
             if (it >= 2) v2_mbar_wait(&bars.da_empty[buf], ((it >> 1) - 1) & 1);
-            for (int j = 0; j < g.n; ++j, ++gc) {
-                const int s = gc % kV2Stages;
+            for (int j = w; j < g.n; j += 4) {
+                const uint32_t c = gc0 + j;
+                const int s = c % kV2Stages;
                 const int vsp = tb.v_sp[j];
                 const int rs = v2_single_span(vsp, C) ? vsp : C;
-                v2_mbar_wait(&bars.v_full[s], (gc / kV2Stages) & 1);
-                const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * l;
-                float part = 0.f;
-#pragma unroll
-                for (int i = 0; i < ITERS; ++i)
-                    if (i < ITERS - 1 || last_ok) part += dot4(*reinterpret_cast<const float4*>(row + 4 * i * G), go[i]);
-                __syncwarp();
-                if ((tid & 31) == 0) v2_mbar_arrive(&bars.v_empty[s]);
-                part = group_sum<G>(part, gm);
-                if (l == 0) s_da[buf][pixel][j] = part;
                 float* dvp = tg.dv[j];
-                if (dvp) {
-                    const float aj = s_a[buf][pixel][j];
-                    dvp += (int64_t)b * tg.v_sb[j] + (int64_t)p * tg.v_sp[j] + 4 * l;
+                const float aj = s_a[buf][pixel][j];
+                if (lt == 0) DW_WAIT(62, v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1));
+                else v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1);
+                const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * qd;
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < ITERS; ++i)
-                        if (i < ITERS - 1 || last_ok)
-                            st_stream4(dvp + 4 * i * G, make_float4(aj * go[i].x, aj * go[i].y, aj * go[i].z, aj * go[i].w));
+                for (int i = 0; i < NC; i += 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        v[u] = (qd + 4 * (i + u) < g.C4) ? *reinterpret_cast<const float4*>(row + 16 * (i + u))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    p0 += dot4(v[0], go[i]); p1 += dot4(v[1], go[i + 1]);
+                    p2 += dot4(v[2], go[i + 2]); p3 += dot4(v[3], go[i + 3]);
+                }
+                __syncwarp();                                   // every lane has read the stage
+                if (lane == 0) v2_mbar_arrive(&bars.v_empty[s]);
+                float part = (p0 + p1) + (p2 + p3);
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                if (qd == 0) s_da[buf][pixel][j] = part;
+                if (dvp) {
+                    dvp += (int64_t)b * tg.v_sb[j] + (int64_t)p * tg.v_sp[j] + 4 * qd;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i)
+                        if (qd + 4 * i < g.C4)
+                            st_stream4(dvp + 16 * i, make_float4(aj * go[i].x, aj * go[i].y, aj * go[i].z, aj * go[i].w));
                 }
             }
+            gc0 += g.n;
             v2_mbar_arrive(&bars.a_empty[buf]);
             v2_mbar_arrive(&bars.da_full[buf]);
+            if (lt == 0 && it < 12) DW_STAMP(50 + it);          // stream: tile it consumed
         }
     }
 }
@@ -1045,9 +1197,9 @@ static int dw_bwd_impl(const char* fn, const SlotPtrs& sp, const SlotGradPtrs& g
         DAVI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int ntiles = g.total_pix / kV2TP;
         const int grid = ntiles < sms ? ntiles : sms;
-        const size_t smem = (size_t)kV2Stages * kV2TP * (C + kV2Slack) * sizeof(float) +
-                            (size_t)2 * kV2TP * n * d * sizeof(float);
-        if (smem <= 200 * 1024)
+        const size_t smem = (size_t)(kV2Stages + 2) * kV2TP * (C + kV2Slack) * sizeof(float) +
+                            (size_t)3 * kV2TP * (n + 1) * d * sizeof(float);
+        if (smem <= 220 * 1024)
         switch ((g.C4 + 15) / 16) {
 #define V2B_CASE(I)                                                                                        \
     case I:                                                                                                \
@@ -1058,7 +1210,7 @@ static int dw_bwd_impl(const char* fn, const SlotPtrs& sp, const SlotGradPtrs& g
             V2B_CASE(3) V2B_CASE(4) V2B_CASE(5) V2B_CASE(6) V2B_CASE(7) V2B_CASE(8)
 #undef V2B_CASE
         }
-        if (smem <= 200 * 1024) return check_launch(fn);
+        if (smem <= 220 * 1024) return check_launch(fn);
     }
     DW_DISPATCH(launch_bwd, sp, gp, q, dout, dq, dscale, g, st);
     return check_launch(fn);
@@ -1185,3 +1337,10 @@ extern "C" int davi_dw_attn_gather(int nprob, const int* m, float* const* out_v,
     DW_DISPATCH(launch_gather, gp, nprob, total_pix, d4, g.C4, (cudaStream_t)stream);
     return check_launch(__func__);
 }
+
+#ifdef DAVI_DW_TRACE
+// trace build only (tools/dw_trace.py): copies the [2][64] clock64 stamps of the last persistent launch to the host
+extern "C" int davi_dw_trace_read(long long* host_2x64) {
+    return cudaMemcpyFromSymbol(host_2x64, davi::g_dw_trace, sizeof(long long) * 128) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -303,6 +303,12 @@ def random_uniform(shape, minval=0.0, maxval=1.0, dtype=None, seed=None, name=No
     return (minval + (maxval - minval) * u).as_subclass(T)
 
 
+def random_normal(shape, mean=0.0, stddev=1.0, dtype=None, seed=None, name=None):
+    """tf.random.normal, drawn from the recorder's stream like every other normal draw (used by the
+    TF-side drop-in tf_ops/davi_tf.py, not by the reference)."""
+    return (mean + stddev * REC.randn(tuple(_flat_ints(shape)), "random_normal")).as_subclass(T)
+
+
 def add_n(xs, name=None):
     r = _t(xs[0])
     for v in xs[1:]:
@@ -847,7 +853,7 @@ def install():
         l2_normalize=l2_normalize, swish=swish, elu=elu)
     linalg = types.SimpleNamespace(matmul=matmul, matvec=matvec)
     image_v1 = types.SimpleNamespace(resize_bilinear=resize_bilinear, resize_nearest_neighbor=resize_nearest)
-    random_ns = types.SimpleNamespace(uniform=random_uniform)
+    random_ns = types.SimpleNamespace(uniform=random_uniform, normal=random_normal)
     dtypes_ns = types.SimpleNamespace(cast=cast)
 
     common = dict(

@@ -1,10 +1,12 @@
 // TensorFlow custom-op shim over the davi C ABI (include/davi.h).
 //
-// STATUS: source only.  TensorFlow (headers and runtime) is absent from the
-// build container and from the GPU boxes, so this file is NOT compiled or run
-// by the test-suite; every line of arithmetic lives behind the C ABI and is
-// exercised through the ctypes binding (deep_attentive_vi_b200/_lib.py).  Where
-// TensorFlow exists, build it with
+// STATUS: TensorFlow (headers and runtime) is absent from the build container
+// and from the GPU boxes, so this file cannot be linked or run here; every line
+// of arithmetic lives behind the C ABI and is exercised through the ctypes
+// binding (deep_attentive_vi_b200/_lib.py).  tests/test_tf_shim.py compiles this
+// file with -fsyntax-only against a stand-in for the op-kernel headers
+// (tf_ops/tf_stub/) so that every C-ABI call site below is type-checked against
+// include/davi.h.  Where TensorFlow exists, build it with
 //
 //   TF_CFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_compile_flags()))')
 //   TF_LFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_link_flags()))')
@@ -201,15 +203,22 @@ REGISTER_KERNEL_BUILDER(Name("DaviNonlocalAttnGrad").Device(tf::DEVICE_GPU), Dav
 // ---------------------------------------------------------------------------
 REGISTER_OP("DaviGaussKl")
     .Input("post: float").Input("prior: float").Input("eps: float")
+    .Input("noise_post: float").Input("noise_prior: float")
     .Attr("post_lo: float").Attr("post_hi: float").Attr("prior_lo: float").Attr("prior_hi: float")
+    .Attr("noise_std_post: float = 0.0").Attr("noise_std_prior: float = 0.0")
     .Attr("has_prior: bool = true")
     .Output("xi: float").Output("kl: float").Output("logq: float").Output("logp: float")
+    .Output("grad: float")
     .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
       c->set_output(0, c->input(2));
       for (int i = 1; i < 4; ++i) c->set_output(i, c->Vector(c->Dim(c->input(2), 0)));
+      c->set_output(4, c->UnknownShapeOfRank(4));
       return tf::Status::OK();
     });
 
+// noise_post / noise_prior: the N(0,1) draws of the train-time GaussianNoise on the log-scales
+// (gaussian_diag.py:165-166), same shape as eps; an EMPTY tensor (0 elements) = no noise.
+// grad [B,W,H,6z]: the whole gradient, emitted by the forward sweep (include/davi.h, davi_gauss_kl_fwd).
 class DaviGaussKlOp : public OpKernel {
  public:
   explicit DaviGaussKlOp(OpKernelConstruction* c) : OpKernel(c) {
@@ -217,65 +226,198 @@ class DaviGaussKlOp : public OpKernel {
     OP_REQUIRES_OK(c, c->GetAttr("post_hi", &qhi_));
     OP_REQUIRES_OK(c, c->GetAttr("prior_lo", &plo_));
     OP_REQUIRES_OK(c, c->GetAttr("prior_hi", &phi_));
+    OP_REQUIRES_OK(c, c->GetAttr("noise_std_post", &nq_));
+    OP_REQUIRES_OK(c, c->GetAttr("noise_std_prior", &np_));
     OP_REQUIRES_OK(c, c->GetAttr("has_prior", &has_prior_));
   }
   void Compute(OpKernelContext* ctx) override {
     const Tensor &post = ctx->input(0), &prior = ctx->input(1), &eps = ctx->input(2);
-    const int B = eps.dim_size(0), Pn = eps.dim_size(1) * eps.dim_size(2), z = eps.dim_size(3);
-    Tensor *xi, *kl, *lq, *lp;
+    const Tensor &n1 = ctx->input(3), &n2 = ctx->input(4);
+    const int B = eps.dim_size(0), W = eps.dim_size(1), H = eps.dim_size(2), z = eps.dim_size(3);
+    const int Pn = W * H;
+    Tensor *xi, *kl, *lq, *lp, *grad;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, eps.shape(), &xi));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({B}), &kl));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(2, TensorShape({B}), &lq));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({B}), &lp));
-    OP_REQUIRES_OK(ctx, Check(davi_gauss_kl_fwd(P(post), has_prior_ ? P(prior) : nullptr, P(eps), nullptr,
-                                                nullptr, P(xi), P(kl), P(lq), P(lp), B, Pn, z, qlo_, qhi_,
-                                                plo_, phi_, 0.f, 0.f, /*grad=*/nullptr, StreamOf(ctx)),
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(4, TensorShape({B, W, H, 6 * z}), &grad));
+    OP_REQUIRES_OK(ctx, Check(davi_gauss_kl_fwd(P(post), has_prior_ ? P(prior) : nullptr, P(eps),
+                                                n1.NumElements() ? P(n1) : nullptr,
+                                                has_prior_ && n2.NumElements() ? P(n2) : nullptr,
+                                                P(xi), P(kl), P(lq), P(lp), B, Pn, z, qlo_, qhi_,
+                                                plo_, phi_, nq_, np_, P(grad), StreamOf(ctx)),
                               "davi_gauss_kl_fwd"));
   }
  private:
-  float qlo_, qhi_, plo_, phi_;
+  float qlo_, qhi_, plo_, phi_, nq_, np_;
   bool has_prior_;
 };
 REGISTER_KERNEL_BUILDER(Name("DaviGaussKl").Device(tf::DEVICE_GPU), DaviGaussKlOp);
 
 REGISTER_OP("DaviGaussKlGrad")
-    .Input("post: float").Input("prior: float").Input("eps: float")
-    .Input("dxi: float").Input("dkl: float")
-    .Attr("post_lo: float").Attr("post_hi: float").Attr("prior_lo: float").Attr("prior_hi: float")
+    .Input("grad: float").Input("dxi: float").Input("dkl: float")
     .Attr("has_prior: bool = true")
     .Output("dpost: float").Output("dprior: float")
     .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
-      c->set_output(0, c->input(0));
-      c->set_output(1, c->input(1));
+      c->set_output(0, c->UnknownShapeOfRank(4));
+      c->set_output(1, c->UnknownShapeOfRank(4));
       return tf::Status::OK();
     });
 
 class DaviGaussKlGradOp : public OpKernel {
  public:
   explicit DaviGaussKlGradOp(OpKernelConstruction* c) : OpKernel(c) {
-    OP_REQUIRES_OK(c, c->GetAttr("post_lo", &qlo_));
-    OP_REQUIRES_OK(c, c->GetAttr("post_hi", &qhi_));
-    OP_REQUIRES_OK(c, c->GetAttr("prior_lo", &plo_));
-    OP_REQUIRES_OK(c, c->GetAttr("prior_hi", &phi_));
     OP_REQUIRES_OK(c, c->GetAttr("has_prior", &has_prior_));
   }
   void Compute(OpKernelContext* ctx) override {
-    const Tensor &post = ctx->input(0), &prior = ctx->input(1), &eps = ctx->input(2);
-    const int B = eps.dim_size(0), Pn = eps.dim_size(1) * eps.dim_size(2), z = eps.dim_size(3);
+    const Tensor &grad = ctx->input(0), &dxi = ctx->input(1), &dkl = ctx->input(2);
+    const int B = grad.dim_size(0), W = grad.dim_size(1), H = grad.dim_size(2), z = grad.dim_size(3) / 6;
     Tensor *dpost, *dprior;
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, post.shape(), &dpost));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, prior.shape(), &dprior));
-    OP_REQUIRES_OK(ctx, Check(davi_gauss_kl_bwd(P(post), has_prior_ ? P(prior) : nullptr, P(eps), nullptr,
-                                                nullptr, P(ctx->input(3)), P(ctx->input(4)), P(dpost),
-                                                has_prior_ ? P(dprior) : nullptr, B, Pn, z, qlo_, qhi_,
-                                                plo_, phi_, 0.f, 0.f, StreamOf(ctx)),
-                              "davi_gauss_kl_bwd"));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B, W, H, 2 * z}), &dpost));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({B, W, H, 2 * z}), &dprior));
+    OP_REQUIRES_OK(ctx, Check(davi_gauss_kl_bwd_saved(P(grad), P(dxi), P(dkl), P(dpost),
+                                                      has_prior_ ? P(dprior) : nullptr, B, W * H, z,
+                                                      StreamOf(ctx)),
+                              "davi_gauss_kl_bwd_saved"));
   }
  private:
-  float qlo_, qhi_, plo_, phi_;
   bool has_prior_;
 };
 REGISTER_KERNEL_BUILDER(Name("DaviGaussKlGrad").Device(tf::DEVICE_GPU), DaviGaussKlGradOp);
+
+// ---------------------------------------------------------------------------
+// DaviLnGelu / DaviLnGeluRes: the LayerNormalization / gelu / gamma-residual glue around the depth-wise
+// attention (model/variational_layer.py:393-412,501-505; model/vae.py:346-348)
+//   mode 0: y = LN(x)    mode 1: y = x + gelu(LN(x))    Res: y = base + res_gamma * (x + gelu(LN(x)))
+// ---------------------------------------------------------------------------
+REGISTER_OP("DaviLnGelu")
+    .Input("x: float").Input("gamma: float").Input("beta: float")
+    .Attr("mode: int = 0").Attr("epsilon: float = 1e-5")
+    .Output("y: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->input(0));
+      return tf::Status::OK();
+    });
+
+class DaviLnGeluOp : public OpKernel {
+ public:
+  explicit DaviLnGeluOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("mode", &mode_));
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &x = ctx->input(0), &g = ctx->input(1), &b = ctx->input(2);
+    const int C = x.dim_size(x.dims() - 1);
+    const tf::int64 rows = x.NumElements() / C;
+    Tensor* y;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x.shape(), &y));
+    OP_REQUIRES_OK(ctx, Check(davi_ln_gelu_fwd(P(x), P(g), P(b), P(y), rows, C, C, C, eps_, mode_, StreamOf(ctx)),
+                              "davi_ln_gelu_fwd"));
+  }
+ private:
+  int mode_;
+  float eps_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviLnGelu").Device(tf::DEVICE_GPU), DaviLnGeluOp);
+
+REGISTER_OP("DaviLnGeluGrad")
+    .Input("x: float").Input("gamma: float").Input("beta: float").Input("dy: float")
+    .Attr("mode: int = 0").Attr("epsilon: float = 1e-5")
+    .Output("dx: float").Output("dgamma: float").Output("dbeta: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      for (int i = 0; i < 3; ++i) c->set_output(i, c->input(i));
+      return tf::Status::OK();
+    });
+
+class DaviLnGeluGradOp : public OpKernel {
+ public:
+  explicit DaviLnGeluGradOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("mode", &mode_));
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &x = ctx->input(0), &g = ctx->input(1), &b = ctx->input(2), &dy = ctx->input(3);
+    const int C = x.dim_size(x.dims() - 1);
+    const tf::int64 rows = x.NumElements() / C;
+    Tensor *dx, *dg, *db, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x.shape(), &dx));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, g.shape(), &dg));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, b.shape(), &db));
+    const size_t wsb = davi_ln_gelu_bwd_workspace_bytes(rows, C);
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, TensorShape({(tf::int64)((wsb + 3) / 4)}), &ws));
+    OP_REQUIRES_OK(ctx, Check(davi_ln_gelu_bwd(P(x), P(g), P(b), P(dy), P(dx), P(dg), P(db), rows, C, C, C, C,
+                                               eps_, mode_, P(&ws), wsb, StreamOf(ctx)),
+                              "davi_ln_gelu_bwd"));
+  }
+ private:
+  int mode_;
+  float eps_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviLnGeluGrad").Device(tf::DEVICE_GPU), DaviLnGeluGradOp);
+
+REGISTER_OP("DaviLnGeluRes")
+    .Input("x: float").Input("gamma: float").Input("beta: float").Input("base: float").Input("res_gamma: float")
+    .Attr("epsilon: float = 1e-5")
+    .Output("y: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->input(0));
+      return tf::Status::OK();
+    });
+
+class DaviLnGeluResOp : public OpKernel {
+ public:
+  explicit DaviLnGeluResOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &x = ctx->input(0), &g = ctx->input(1), &b = ctx->input(2), &base = ctx->input(3);
+    const int C = x.dim_size(x.dims() - 1);
+    const tf::int64 rows = x.NumElements() / C;
+    Tensor* y;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x.shape(), &y));
+    OP_REQUIRES_OK(ctx, Check(davi_ln_gelu_res_fwd(P(x), P(g), P(b), P(base), P(ctx->input(4)), P(y), rows, C,
+                                                   C, C, C, eps_, StreamOf(ctx)),
+                              "davi_ln_gelu_res_fwd"));
+  }
+ private:
+  float eps_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviLnGeluRes").Device(tf::DEVICE_GPU), DaviLnGeluResOp);
+
+REGISTER_OP("DaviLnGeluResGrad")
+    .Input("x: float").Input("gamma: float").Input("beta: float").Input("res_gamma: float").Input("dy: float")
+    .Attr("epsilon: float = 1e-5")
+    .Output("dx: float").Output("dgamma: float").Output("dbeta: float").Output("dres_gamma: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      for (int i = 0; i < 4; ++i) c->set_output(i, c->input(i));
+      return tf::Status::OK();
+    });
+
+class DaviLnGeluResGradOp : public OpKernel {
+ public:
+  explicit DaviLnGeluResGradOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &x = ctx->input(0), &g = ctx->input(1), &b = ctx->input(2), &rg = ctx->input(3);
+    const Tensor& dy = ctx->input(4);
+    const int C = x.dim_size(x.dims() - 1);
+    const tf::int64 rows = x.NumElements() / C;
+    Tensor *dx, *dg, *db, *drg, ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x.shape(), &dx));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, g.shape(), &dg));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, b.shape(), &db));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({}), &drg));
+    const size_t wsb = davi_ln_gelu_bwd_workspace_bytes(rows, C);
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, TensorShape({(tf::int64)((wsb + 3) / 4)}), &ws));
+    OP_REQUIRES_OK(ctx, Check(davi_ln_gelu_res_bwd(P(x), P(g), P(b), P(rg), P(dy), P(dx), P(dg), P(db), P(drg),
+                                                   rows, C, C, C, C, eps_, P(&ws), wsb, StreamOf(ctx)),
+                              "davi_ln_gelu_res_bwd"));
+  }
+ private:
+  float eps_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviLnGeluResGrad").Device(tf::DEVICE_GPU), DaviLnGeluResGradOp);
 
 // ---------------------------------------------------------------------------
 // DaviDlmNll / DaviBernoulliNll: data negative log-likelihood with the

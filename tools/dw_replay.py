@@ -127,21 +127,41 @@ def build(e, dev):
     return launch, [keep, tabs, mt]
 
 
-def time_entry(e, dev, reps=3, footprint=3 * L2_BYTES):
+def time_entry(e, dev, reps=3, footprint=3 * L2_BYTES, graph=True):
     """Mean time (ms) of one launch of entry e with cold inputs: the launch is issued back to back on ROTATING
     operand sets whose total footprint exceeds 3x L2, all between ONE pair of CUDA events on the launching
-    stream; median of `reps` rounds."""
+    stream; median of `reps` rounds.  The launches are replayed from a captured CUDA graph, the way the training
+    step issues them (a ctypes call costs the host ~10 us, more than the small kernels run)."""
     per_set = max(moved_bytes(e), 1)
     sets = max(2, min(24, int(footprint // per_set) + 1))
     built = [build(e, dev) for _ in range(sets)]
     for fn, _ in built:
         fn()
+    torch.cuda.synchronize()
+    run = None
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            for fn, _ in built:
+                fn()
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                for fn, _ in built:
+                    fn()
+        torch.cuda.current_stream().wait_stream(side)
+        run = g.replay
+        run()
+    else:
+        def run():
+            for fn, _ in built:
+                fn()
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for fn, _ in built:
-            fn()
+        run()
         e1.record()
         e1.synchronize()
         ts.append(e0.elapsed_time(e1) / sets)
