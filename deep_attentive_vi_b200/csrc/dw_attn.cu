@@ -16,6 +16,7 @@
 //     of the reference never exist.
 // Algorithmic bytes: fwd 4*B*P*(n*(d+C)+d+C), bwd
 // 4*B*P*(2n(d+C)+2d+C); the kernels touch each of those bytes once.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -39,6 +40,14 @@ __device__ long long g_dw_trace[2][64];
         if ((threadIdx.x & 31) == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))      \
             g_dw_trace[blockIdx.x != 0][i] += clock64() - t0_;                                \
     } while (0)
+// every lane runs stmt; the lanes for which cond holds (one per role) record its duration
+#define DW_WAIT_IF(cond, i, stmt)                                                             \
+    do {                                                                                      \
+        const long long t0_ = clock64();                                                      \
+        stmt;                                                                                 \
+        if ((cond) && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))                       \
+            g_dw_trace[blockIdx.x != 0][i] += clock64() - t0_;                                \
+    } while (0)
 #define DW_TRACE_CLEAR()                                                                      \
     do {                                                                                      \
         if (threadIdx.x < 64 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))             \
@@ -52,6 +61,10 @@ __device__ long long g_dw_trace[2][64];
 #define DW_WAIT(i, stmt) \
     do {                 \
         stmt;            \
+    } while (0)
+#define DW_WAIT_IF(cond, i, stmt) \
+    do {                          \
+        stmt;                     \
     } while (0)
 #define DW_TRACE_CLEAR() \
     do {                 \
@@ -271,9 +284,14 @@ __device__ __forceinline__ void v2_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(v2_smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __noinline__ void v2_wait_timed_out(const uint64_t* bar, uint32_t parity) {
+    printf("davi dw_attn: mbarrier wait timed out (block %d thread %d barrier offset %u parity %u)\n", (int)blockIdx.x,
+           (int)threadIdx.x, v2_smem_u32(bar), parity);
+    __trap();                                                  // never hang the GPU: fail the launch instead
+}
 __device__ __forceinline__ void v2_mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
-    const long long t0 = clock64();
+    long long t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t"
@@ -285,7 +303,8 @@ __device__ __forceinline__ void v2_mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(v2_smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();      // never hang the GPU: fail the launch instead
+        if (t0 == 0) t0 = clock64();                           // the clock is only read once the first try failed
+        else if (clock64() - t0 > 2000000000ll) v2_wait_timed_out(bar, parity);
     }
 }
 __device__ __forceinline__ void v2_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -318,6 +337,8 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
     float* ring = reinterpret_cast<float*>(v2_smem);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    DW_TRACE_CLEAR();
+    if (tid == 0) DW_STAMP(0);                                  // entry
     if (tid < DAVI_MAX_SLOTS) {
         const int j = tid;
         tb.k[j] = sp.k[j]; tb.v[j] = sp.v[j];
@@ -329,6 +350,7 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
     if (tid >= 64 && tid < 66) { v2_mbar_init(&bars.a_full[tid - 64], 128); v2_mbar_init(&bars.a_empty[tid - 64], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    if (tid == 0) DW_STAMP(1);                                  // barriers + tables ready
 
     if (warp == 0) {
         // ---------------- producer: one thread issues every bulk copy ----------------
@@ -339,7 +361,8 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
                 const int b = pix0 / g.P, p0 = pix0 - b * g.P;
                 for (int j = 0; j < g.n; ++j, ++gc) {
                     const int s = gc % kV2Stages;
-                    if (gc >= kV2Stages) v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1);
+                    if (gc == kV2Stages) DW_STAMP(2);           // producer: ring filled once
+                    if (gc >= kV2Stages) DW_WAIT(4, v2_mbar_wait(&bars.v_empty[s], ((gc / kV2Stages) - 1) & 1));
                     const int vsp = tb.v_sp[j];
                     const float* src = tb.v[j] + (int64_t)b * tb.v_sb[j] + (int64_t)p0 * vsp;
                     float* dst = ring + (size_t)s * stage_floats;
@@ -368,7 +391,9 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
             float a[SPL];
             dw_scores<G, SPL>(tb, g, l, b, p, q + (int64_t)pix * g.q_sp, a, nullptr, gm, scale);
             const int buf = it & 1;
-            if (it >= 2) v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1);
+            if (it >= 2) {
+                DW_WAIT_IF(lt == 0, 6, v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1));
+            }
 #pragma unroll
             for (int u = 0; u < SPL; ++u) {
                 const int j = l + u * G;
@@ -378,6 +403,7 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
                 }
             }
             v2_mbar_arrive(&bars.a_full[buf]);          // arrive has release semantics for the stores above
+            if (lt == 0 && it < 12) DW_STAMP(8 + it);           // score: weights of tile it published
         }
     } else {
         // ---------------- stream warps: out = sum_j a_j * V_j over the staged tiles ----------------
@@ -387,7 +413,7 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
         uint32_t gc = 0, it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int buf = it & 1;
-            v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1);
+            DW_WAIT_IF(lt == 0, 61, v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1));
             float4 acc[ITERS];
 #pragma unroll
             for (int i = 0; i < ITERS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -404,7 +430,7 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
                         const int vsp = tb.v_sp[j];
                         const int rs = v2_single_span(vsp, C) ? vsp : C;
                         aj[u] = s_a[buf][pixel][j];
-                        v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1);
+                        DW_WAIT_IF(lt == 0, 62, v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1));
                         const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * l;
 #pragma unroll
                         for (int i = 0; i < ITERS; ++i)
@@ -428,6 +454,7 @@ dw_attn_fwd_v2_kernel(const SlotPtrs sp, const float* __restrict__ q, float* __r
 #pragma unroll
             for (int i = 0; i < ITERS; ++i)
                 if (i < ITERS - 1 || last_ok) st_stream4(op + 4 * i * G, acc[i]);
+            if (lt == 0 && it < 12) DW_STAMP(50 + it);          // stream: tile it consumed and written
         }
     }
 }
@@ -762,8 +789,7 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
         auto finish = [&](int pix, uint32_t itp) {
             const int buf = itp & 1;
             const int b = pix / g.P, p = pix - b * g.P;
-            if (lt == 0) DW_WAIT(5, v2_mbar_wait(&bars.da_full[buf], (itp >> 1) & 1));
-            else v2_mbar_wait(&bars.da_full[buf], (itp >> 1) & 1);
+            DW_WAIT_IF(lt == 0, 5, v2_mbar_wait(&bars.da_full[buf], (itp >> 1) & 1));
             float da[SPL], ds[SPL];
             float dsum = 0.f;
 #pragma unroll
@@ -859,8 +885,7 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
                 for (int u = 0; u < SPL; ++u) a[u] *= inv;
             }
             if (it >= 2) {
-                if (lt == 0) DW_WAIT(6, v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1));
-                else v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1);
+                DW_WAIT_IF(lt == 0, 6, v2_mbar_wait(&bars.a_empty[buf], ((it >> 1) - 1) & 1));
             }
 #pragma unroll
             for (int u = 0; u < SPL; ++u) {
@@ -883,7 +908,7 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
         }
     } else {
         // ---------------- stream warps: da_j = <V_j, g>, dV_j = a_j g over the staged tiles ----------------
-        // ONE warp owns a whole staged tile (slot j of the tile goes to warp j % 4), so four tiles are consumed
+        // ONE warp owns a whole staged tile (ring stage c goes to warp c % 4), so four tiles are consumed
         // concurrently and the per-stage overhead (wait, release, reduction, addressing: ~130 instructions of a
         // lone warp, which bound the first version at ~700 cycles / stage) is paid once per 9 KB instead of four
         // times.  Lane = (pixel, quarter): a lane covers float4 columns quarter, quarter + 4, ... of its pixel's
@@ -900,8 +925,7 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
             const int b = pix / g.P, p = pix - b * g.P;
             float4 go[NC];
             {
-                if (lt == 0) DW_WAIT(60, v2_mbar_wait(&bars.go_full[buf], (it >> 1) & 1));
-                else v2_mbar_wait(&bars.go_full[buf], (it >> 1) & 1);
+                DW_WAIT_IF(lt == 0, 60, v2_mbar_wait(&bars.go_full[buf], (it >> 1) & 1));
                 const float* row = gbuf + (size_t)buf * stage_floats + pixel * orow + 4 * qd;
 #pragma unroll
                 for (int i = 0; i < NC; ++i)
@@ -911,18 +935,20 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
                 if (lane == 0) v2_mbar_arrive(&bars.go_empty[buf]);
             }
             if (lt == 0 && it < 12) DW_STAMP(36 + it);          // stream: dOut tile of tile it received
-            if (lt == 0) DW_WAIT(61, v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1));
-            else v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1);
+            DW_WAIT_IF(lt == 0, 61, v2_mbar_wait(&bars.a_full[buf], (it >> 1) & 1));
             if (it >= 2) v2_mbar_wait(&bars.da_empty[buf], ((it >> 1) - 1) & 1);
-            for (int j = w; j < g.n; j += 4) {
+            // warp w takes the ring stages c with c % 4 == w (NOT the slots j with j % 4 == w): every ring stage then
+            // has ONE consumer warp for all of its uses, which sees them in order.  With slot-indexed ownership the
+            // next use of a stage could belong to another warp, and a parity wait issued a whole phase early (an
+            // older copy landing after younger ones) passes at once -- a rare stale read + double release.
+            for (int j = (int)((w - gc0) & 3u); j < g.n; j += 4) {
                 const uint32_t c = gc0 + j;
                 const int s = c % kV2Stages;
                 const int vsp = tb.v_sp[j];
                 const int rs = v2_single_span(vsp, C) ? vsp : C;
                 float* dvp = tg.dv[j];
                 const float aj = s_a[buf][pixel][j];
-                if (lt == 0) DW_WAIT(62, v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1));
-                else v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1);
+                DW_WAIT_IF(lt == 0, 62, v2_mbar_wait(&bars.v_full[s], (c / kV2Stages) & 1));
                 const float* row = ring + (size_t)s * stage_floats + pixel * rs + 4 * qd;
                 float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
@@ -954,6 +980,167 @@ dw_attn_bwd_v2_kernel(const SlotPtrs sp, const SlotGradPtrs gp, const float* __r
             v2_mbar_arrive(&bars.da_full[buf]);
             if (lt == 0 && it < 12) DW_STAMP(50 + it);          // stream: tile it consumed
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// n <= 5 (the first layers: 24-73 MB per call).  These calls are bound by the length of a CTA's dependent
+// chain, not by bytes: the streaming kernels above take one DRAM round trip for the key rows, then one per batch
+// of UNROLL value rows.  Here EVERY load of the pixel -- value rows of all slots, dOut, key rows, query -- is
+// issued before the first use (nothing depends on the scores but the arithmetic), so a CTA pays ONE round trip.
+// Lane l owns the score of slot l (n <= NMAX <= G); the slot table is read straight from the launch parameters.
+// ---------------------------------------------------------------------------------------
+template <int G, int ITERS, int NMAX>
+__global__ void __launch_bounds__(kDwThreads, NMAX <= 2 ? 4 : 2)
+dw_attn_fwd_tiny_kernel(const __grid_constant__ SlotPtrs sp, const float* __restrict__ q, float* __restrict__ out,
+                        float* __restrict__ attn, const __grid_constant__ DwGeom g) {
+    const int l = threadIdx.x & (G - 1);
+    const int gbase = (threadIdx.x & 31) & ~(G - 1);
+    const int pix = (blockIdx.x * kDwThreads + threadIdx.x) / G;
+    if (pix >= g.total_pix) return;
+    const int b = pix / g.P, p = pix - b * g.P;
+    const bool last_ok = (l + (ITERS - 1) * G) < g.C4;
+    const unsigned gm = group_mask<G>();
+
+    float4 v[NMAX][ITERS];
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+        const float* vp = (j < g.n) ? sp.v[j] + (int64_t)b * sp.v_sb[j] + (int64_t)p * sp.v_sp[j] + 4 * l : nullptr;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it)
+            v[j][it] = (vp && (it < ITERS - 1 || last_ok)) ? ld_stream4(vp + 4 * it * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float scale = g.scale_ptr ? __ldg(g.scale_ptr) : 1.f;
+    float s = -INFINITY;
+    if (l < g.n) {      // d <= 32 (dispatch): the whole key row and query row are requested at once
+        const float* kp = sp.k[l] + (int64_t)b * sp.k_sb[l] + (int64_t)p * sp.k_sp[l];
+        const float* qp = q + (int64_t)pix * g.q_sp;
+        float4 kv[8], qv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < g.d4) { kv[c] = ld4(kp + 4 * c); qv[c] = ld4(qp + 4 * c); }
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < g.d4) dot += dot4(kv[c], qv[c]);
+        s = dot * scale;
+    }
+    const float m = group_max<G>(s, gm);
+    float a = (l < g.n) ? __expf(s - m) : 0.f;
+    a *= 1.f / group_sum<G>(a, gm);
+    if (attn && l < g.n) attn[(int64_t)pix * g.n + l] = a;
+
+    float4 acc[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+        const float aj = __shfl_sync(gm, a, gbase + j);
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) fma4(acc[it], aj, v[j][it]);
+    }
+    float* op = out + (int64_t)pix * g.o_sp + 4 * l;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+        if (it < ITERS - 1 || last_ok) st_stream4(op + 4 * it * G, acc[it]);
+}
+
+template <int G, int ITERS, int NMAX>
+__global__ void __launch_bounds__(kDwThreads, NMAX <= 2 ? 3 : 2)
+dw_attn_bwd_tiny_kernel(const __grid_constant__ SlotPtrs sp, const __grid_constant__ SlotGradPtrs gp,
+                        const float* __restrict__ q, const float* __restrict__ dout, float* __restrict__ dq,
+                        float* __restrict__ dscale, const __grid_constant__ DwGeom g) {
+    __shared__ float red[32];
+    const int l = threadIdx.x & (G - 1);
+    const int gbase = (threadIdx.x & 31) & ~(G - 1);
+    const int pix = (blockIdx.x * kDwThreads + threadIdx.x) / G;
+    float dsc_local = 0.f;
+    if (pix < g.total_pix) {
+        const int b = pix / g.P, p = pix - b * g.P;
+        const bool last_ok = (l + (ITERS - 1) * G) < g.C4;
+        const bool kcol = l < g.d4;
+        const unsigned gm = group_mask<G>();
+        const float* qp = q + (int64_t)pix * g.q_sp;
+
+        float4 go[ITERS], v[NMAX][ITERS], kc[NMAX];
+        {
+            const float* gpx = dout + (int64_t)pix * g.o_sp + 4 * l;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it)
+                go[it] = (it < ITERS - 1 || last_ok) ? ld_stream4(gpx + 4 * it * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            const bool on = j < g.n;
+            const float* vp = on ? sp.v[j] + (int64_t)b * sp.v_sb[j] + (int64_t)p * sp.v_sp[j] + 4 * l : nullptr;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it)
+                v[j][it] = (on && (it < ITERS - 1 || last_ok)) ? ld_stream4(vp + 4 * it * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // float4 column l of key row j, for dq (the same lines the score loads below touch)
+            kc[j] = (on && kcol) ? ld4(sp.k[j] + (int64_t)b * sp.k_sb[j] + (int64_t)p * sp.k_sp[j] + 4 * l)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float scale = g.scale_ptr ? __ldg(g.scale_ptr) : 1.f;
+        float r = 0.f, s = -INFINITY;
+        if (l < g.n) {
+            const float* kp = sp.k[l] + (int64_t)b * sp.k_sb[l] + (int64_t)p * sp.k_sp[l];
+            float4 kv[8], qw[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < g.d4) { kv[c] = ld4(kp + 4 * c); qw[c] = ld4(qp + 4 * c); }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < g.d4) r += dot4(kv[c], qw[c]);
+            s = r * scale;
+        }
+        const float4 qv = kcol ? ld4(qp + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float m = group_max<G>(s, gm);
+        float a = (l < g.n) ? __expf(s - m) : 0.f;
+        a *= 1.f / group_sum<G>(a, gm);
+
+        float da = 0.f;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            float part = 0.f;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) part += dot4(v[j][it], go[it]);
+            part = group_sum<G>(part, gm);
+            if (l == j) da = part;
+        }
+        const float dsum = group_sum<G>(a * da, gm);
+        const float ds = a * (da - dsum);
+        dsc_local = ds * r;
+        if (g.attn_out && l < g.n) {
+            g.attn_out[(int64_t)pix * g.n + l] = a;
+            g.ds_out[(int64_t)pix * g.n + l] = ds * scale;
+        }
+        float4 dqv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            if (j >= g.n) break;
+            const float aj = __shfl_sync(gm, a, gbase + j);
+            const float dsj = __shfl_sync(gm, ds, gbase + j) * scale;
+            float* dvp = gp.dv[j];
+            if (dvp) {
+                dvp += (int64_t)b * gp.v_sb[j] + (int64_t)p * gp.v_sp[j] + 4 * l;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it)
+                    if (it < ITERS - 1 || last_ok)
+                        st_stream4(dvp + 4 * it * G, make_float4(aj * go[it].x, aj * go[it].y, aj * go[it].z, aj * go[it].w));
+            }
+            if (kcol) {
+                fma4(dqv, dsj, kc[j]);
+                float* dkp = gp.dk[j];
+                if (dkp)
+                    *reinterpret_cast<float4*>(dkp + (int64_t)b * gp.k_sb[j] + (int64_t)p * gp.k_sp[j] + 4 * l) =
+                        make_float4(dsj * qv.x, dsj * qv.y, dsj * qv.z, dsj * qv.w);
+            }
+        }
+        if (kcol && dq) *reinterpret_cast<float4*>(dq + (int64_t)pix * g.q_sp + 4 * l) = dqv;
+    }
+    if (dscale) {  // uniform branch: every thread of the block reaches the barrier
+        const float tot = block_sum(dsc_local, red);
+        if (threadIdx.x == 0) atomicAdd(dscale, tot);
     }
 }
 
@@ -1093,7 +1280,9 @@ static void launch_fwd(const SlotPtrs& sp, const float* q, float* out, float* at
                        cudaStream_t st) {
     const int64_t threads = (int64_t)g.total_pix * G;
     const int grid = (int)((threads + kDwThreads - 1) / kDwThreads);
-    if (g.n <= 2) dw_attn_fwd_small_kernel<G, ITERS, 1><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
+    if (g.d4 <= 8 && g.n <= 2) dw_attn_fwd_tiny_kernel<G, ITERS, 2><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
+    else if (g.d4 <= 8 && g.n <= 5) dw_attn_fwd_tiny_kernel<G, ITERS, 5><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
+    else if (g.n <= 2) dw_attn_fwd_small_kernel<G, ITERS, 1><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
     else if (g.n <= 5) dw_attn_fwd_small_kernel<G, ITERS, 2><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
     else dw_attn_fwd_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(sp, q, out, attn, g);
 }
@@ -1102,7 +1291,9 @@ static void launch_bwd(const SlotPtrs& sp, const SlotGradPtrs& gp, const float* 
                        float* dq, float* dscale, const DwGeom& g, cudaStream_t st) {
     const int64_t threads = (int64_t)g.total_pix * G;
     const int grid = (int)((threads + kDwThreads - 1) / kDwThreads);
-    if (g.n <= 2) dw_attn_bwd_small_kernel<G, ITERS, 1><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
+    if (g.acc_mask == 0 && g.d4 <= 8 && g.n <= 2) dw_attn_bwd_tiny_kernel<G, ITERS, 2><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
+    else if (g.acc_mask == 0 && g.d4 <= 8 && g.n <= 5) dw_attn_bwd_tiny_kernel<G, ITERS, 5><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
+    else if (g.n <= 2) dw_attn_bwd_small_kernel<G, ITERS, 1><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
     else if (g.n <= 5) dw_attn_bwd_small_kernel<G, ITERS, 2><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
     else dw_attn_bwd_kernel<G, ITERS><<<grid, kDwThreads, 0, st>>>(sp, gp, q, dout, dq, dscale, g);
 }
@@ -1190,8 +1381,8 @@ static int dw_bwd_impl(const char* fn, const SlotPtrs& sp, const SlotGradPtrs& g
     }
     if (dscale) DAVI_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
     // same crossover as the forward; the bulk-copy kernel has no read-modify-write (accumulate) variant
-    if (dw_v2_enabled() && g.acc_mask == 0 && g.C4 > 32 && g.C4 <= 80 && P % kV2TP == 0 && n >= 8 &&
-        (int64_t)n * g.total_pix >= 10 * 10240) {
+    if (dw_v2_enabled() && g.acc_mask == 0 && g.C4 > 32 && g.C4 <= 80 && P % kV2TP == 0 && n >= 6 &&
+        (int64_t)n * g.total_pix >= 6 * 10240) {
         int dev = 0, sms = 0;
         DAVI_CUDA(cudaGetDevice(&dev));
         DAVI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

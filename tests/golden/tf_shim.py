@@ -778,6 +778,10 @@ class MultivariateNormalDiag(Distribution):
         Distribution.__init__(self, reparameterization_type=FULLY_REPARAMETERIZED, name="MVNDiag")
         self.loc, self.scale = _t(loc), _t(scale_diag)
 
+    @property
+    def batch_shape(self):                             # TFP: every axis but the event (last) one
+        return TensorShape(torch.broadcast_shapes(self.loc.shape, self.scale.shape)[:-1])
+
     def sample(self, sample_shape=(), seed=None):
         ss = _flat_ints(sample_shape) if not isinstance(sample_shape, int) else [sample_shape]
         eps = REC.randn(tuple(ss) + tuple(self.loc.size()), "mvn_sample")

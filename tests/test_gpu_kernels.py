@@ -570,3 +570,37 @@ def test_gauss_kl_saved_gradient_equals_recomputed_gradient(cuda, B, P, z, has_p
     assert rel_err(a, a2) < 2e-6
     if has_prior:
         assert rel_err(b, b2) < 2e-6
+
+
+@pytest.mark.parametrize("n", [6, 10, 13])
+def test_dw_attn_bulk_copy_backward_is_reproducible_under_back_to_back_launches(cuda, n):
+    """The persistent backward consumes its shared-memory ring with one warp per staged tile.  A ring stage must keep
+    ONE consumer warp over all of its uses (stage index, not slot index, picks the warp); otherwise a warp can wait
+    for the next use of a stage a whole barrier phase early and read stale data -- seen once per ~2 000 launches
+    when n % 4 != 0.  300 back-to-back launches on rotating operand sets must all return the bits of the first."""
+    from deep_attentive_vi_b200 import _lib
+    B, P, d, C = 40, 256, 20, 276
+    torch.manual_seed(n)
+    sets = []
+    for _ in range(3):
+        q, k, v = torch.randn(B, P, d, device=cuda), torch.randn(B, n, P, d, device=cuda), torch.randn(B, n, P, C, device=cuda)
+        go = torch.randn(B, P, C, device=cuda)
+        sets.append((q, k, v, go, torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)))
+    st = torch.cuda.current_stream().cuda_stream
+
+    def launch(s):
+        q, k, v, go, dq, dk, dv = s
+        _lib.call("davi_dw_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), go.data_ptr(), dq.data_ptr(),
+                  dk.data_ptr(), dv.data_ptr(), 0, B, n, P, d, C, d, n * P * d, P * d, d, n * P * C, P * C, C, C, 0, st)
+
+    first = []
+    for s in sets:
+        launch(s)
+        first.append(tuple(t.clone() for t in s[4:]))
+    for rep in range(100):
+        for s in sets:
+            launch(s)
+        if rep % 20 == 19:
+            for s, f in zip(sets, first):
+                for a, b in zip(s[4:], f):
+                    assert torch.equal(a, b), rep
