@@ -91,6 +91,59 @@ def cosine_warmup_lr(step, steps_per_epoch, lr, min_lr, warmup_epochs, decay_epo
     return lr * ((1.0 - alpha) * cosine + alpha)
 
 
+class GradBuckets:
+    """Plan + bookkeeping of the bucketed gradient all-reduce (~25 MB buckets launched as the backward
+    produces them).  Pure host logic, no device code.
+
+    `sources`: {key: [(lo, hi), ...]} -- the ranges of the flat gradient array a gradient source writes once its
+    tensor has arrived (a plain parameter: its own range; the effective kernel of a weight-normed convolution: the
+    ranges of its v and log_g).  Buckets are contiguous slices of the flat array, cut at multiples of `bucket_floats`
+    but never inside the hull of one source, so a source feeds exactly ONE bucket.  `arrived(key)` returns the
+    bucket that has just become complete (or None); `remaining()` lists the incomplete ones in order."""
+
+    def __init__(self, sources, total, bucket_floats):
+        hulls = sorted((min(lo for lo, _ in r), max(hi for _, hi in r), k) for k, r in sources.items())
+        merged = []                                   # overlapping hulls form one atom
+        for lo, hi, k in hulls:
+            if merged and lo < merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+                merged[-1][2].append(k)
+            else:
+                merged.append([lo, hi, [k]])
+        self.bounds, self.members = [], []            # [(lo, hi)], [[key, ...]]
+        start, keys = 0, []
+        for lo, hi, ks in merged:
+            if keys and hi - start > bucket_floats and lo > start:
+                self.bounds.append((start, lo)); self.members.append(keys)
+                start, keys = lo, []
+            keys = keys + ks
+        self.bounds.append((start, total)); self.members.append(keys)
+        self.bucket_of = {k: b for b, ks in enumerate(self.members) for k in ks}
+        self.reset()
+
+    def reset(self):
+        self.pending = [len(ks) for ks in self.members]
+        self.seen = set()
+        self.done = [False] * len(self.members)
+
+    def arrived(self, key):
+        if key in self.seen or key not in self.bucket_of:
+            return None
+        self.seen.add(key)
+        b = self.bucket_of[key]
+        self.pending[b] -= 1
+        if self.pending[b] == 0 and not self.done[b]:
+            self.done[b] = True
+            return b
+        return None
+
+    def remaining(self):
+        out = [b for b, d in enumerate(self.done) if not d]
+        for b in out:
+            self.done[b] = True
+        return out
+
+
 class FlatState:
     """Re-homes every trainable parameter into a flat fp32 array (grouped by regulariser strength)
     with flat gradient / Adamax-moment arrays of the same layout.  Gradients are NOT accumulated
@@ -146,11 +199,13 @@ class FlatState:
         rv, rg, rw, rc = [], [], [], []
         woff = 0
         sizes = []
+        self.wn_index = []      # per module: (W offset, W numel, v offset, log_g offset, rows, first row in the tables)
         for m in mods:
             o, i, h, w = m.v.shape
             cols = i * h * w
             v_off = (m.v.data_ptr() - base) // 4
             g_off = (m.log_g.data_ptr() - base) // 4
+            self.wn_index.append((woff, o * cols, v_off, g_off, o, len(rv)))
             for r in range(o):
                 rv.append(v_off + r * cols); rg.append(g_off + r); rw.append(woff + r * cols); rc.append(cols)
             sizes.append((m, woff, o, i, h, w))
@@ -197,12 +252,12 @@ class FlatState:
         for t, _, _, _, _ in self.slots:
             t.grad = None
 
-    def gather_grads(self, stream):
-        """Copy every deposited gradient into its place in G (parameters) or dW (effective conv
-        kernels).  Conv gradients are stored like their weights: OHWI (channels_last) memory order."""
+    def gather_grads(self, stream, slots=None):
+        """Copy every deposited gradient (of `slots`, default all) into its place in G (parameters) or dW
+        (effective conv kernels).  Conv gradients are stored like their weights: OHWI (channels_last) memory order."""
         for which, flat in (("G", self.G), ("dW", getattr(self, "dW", None))):
             ptrs, offs, sizes, keep = [], [], [], []
-            for t, w, off, n, is_conv in self.slots:
+            for t, w, off, n, is_conv in (self.slots if slots is None else slots):
                 g = t.grad
                 if w != which or g is None:
                     continue
@@ -222,6 +277,46 @@ class FlatState:
             _lib.call("davi_multi_copy", pt, ot, st_, len(order), flat.data_ptr(), stream)
             _lib.add_launches((len(order) + 63) // 64 - 1)
 
+    def weight_norm_bwd(self, stream, row_lo=0, row_hi=None):
+        """dW -> gradients of v and log_g for the table rows [row_lo, row_hi) (default: all)."""
+        rv, rg, rw, rc = self.wn_tables
+        row_hi = self.wn_rows if row_hi is None else row_hi
+        if row_hi > row_lo:
+            _lib.call("davi_weight_norm_bwd", self.P.data_ptr(), self.dW.data_ptr(), self.G.data_ptr(),
+                      rv[row_lo:].data_ptr(), rg[row_lo:].data_ptr(), rw[row_lo:].data_ptr(), rc[row_lo:].data_ptr(),
+                      row_hi - row_lo, stream)
+
+    def plan_buckets(self, bucket_floats):
+        """-> (GradBuckets, per bucket: slots to gather + weight-norm row range).  Sources are the tensors autograd
+        deposits gradients in: plain parameters (but not the v / log_g of a convolution whose kernel is read from
+        W: their gradient comes out of davi_weight_norm_bwd) and the leaf views of W."""
+        wn_param_ranges = set()
+        for woff, wn, v_off, g_off, o, row0 in getattr(self, "wn_index", []):
+            wn_param_ranges.add(v_off); wn_param_ranges.add(g_off)
+        sources, slot_of = {}, {}
+        for slot in self.slots:
+            t, which, off, n, _ = slot
+            if which == "G":
+                if off in wn_param_ranges:
+                    continue
+                sources[id(t)] = [(off, off + n)]
+            else:
+                ranges = []
+                for woff, wn, v_off, g_off, o, row0 in self.wn_index:
+                    if off <= woff < off + n:
+                        ranges += [(v_off, v_off + wn), (g_off, g_off + o)]
+                sources[id(t)] = ranges
+            slot_of[id(t)] = slot
+        plan = GradBuckets(sources, self.G.numel(), bucket_floats)
+        per = []
+        for (lo, hi), keys in zip(plan.bounds, plan.members):
+            rows = [(row0, row0 + o) for woff, wn, v_off, g_off, o, row0 in getattr(self, "wn_index", [])
+                    if lo <= v_off < hi]
+            assert all(lo <= g_off < hi for woff, wn, v_off, g_off, o, row0 in getattr(self, "wn_index", [])
+                       if lo <= v_off < hi), "a convolution's v and log_g must share a bucket"
+            per.append({"slots": [slot_of[k] for k in keys], "rows": rows, "range": (lo, hi)})
+        return plan, per
+
     def release(self):
         """Detach the model from the fused weight-norm path (it computes its kernels itself again)."""
         for m in getattr(self, "wn_modules", []):
@@ -239,7 +334,7 @@ class Trainer:
     device memory (input batch, KL weight beta, Adamax step size)."""
 
     def __init__(self, model, hparams=None, device="cuda", world_size=1, rank=0, train_size=None, batch_size=None,
-                 use_graph=False, graph_warmup=3, use_schedule=True):
+                 use_graph=False, graph_warmup=3, use_schedule=True, bucket_mb=None):
         """train_size / batch_size (per GPU): when given, the schedule lengths are derived like keras_train does
         (tr.py:139-140): lr_steps_per_epoch = int(train_size / (num_gpus * batch_size)), lr_decay_epochs =
         epochs - lr_warmup_epochs; otherwise the hparams' own values are used."""
@@ -274,6 +369,51 @@ class Trainer:
         # capture needs every autograd node (AccumulateGrad included) to have been created on a
         # non-default stream: the eager warm-up steps of a graphed trainer run on this side stream
         self._side = torch.cuda.Stream(device=self.device) if use_graph else None
+        # bucketed gradient all-reduce overlapped with the backward (world > 1; bucket_mb = 0 keeps the single
+        # all-reduce after the backward, a value forces the bucketed path even on one rank -- tests)
+        self.bucket_mb = (32 if world_size > 1 else 0) if bucket_mb is None else bucket_mb
+        self._buckets = None
+        if self.bucket_mb:
+            self._setup_buckets()
+
+    def _setup_buckets(self):
+        st = self.state
+        self._plan, self._bucket_work = st.plan_buckets(int(self.bucket_mb * 1e6 / 4))
+        for b in self._bucket_work:                     # contiguous runs of weight-norm table rows
+            runs = []
+            for lo, hi in sorted(b["rows"]):
+                if runs and runs[-1][1] == lo:
+                    runs[-1][1] = hi
+                else:
+                    runs.append([lo, hi])
+            b["rows"] = runs
+        self._buckets = True
+        self._bucketing = False
+        self._works = []
+        self.bucket_log = []                            # (bucket, sources still outstanding in OTHER buckets) per flush
+        for t, _, _, _, _ in st.slots:
+            if id(t) in self._plan.bucket_of:
+                t.register_post_accumulate_grad_hook(self._grad_arrived)
+
+    def _grad_arrived(self, t):
+        if not self._bucketing:
+            return
+        b = self._plan.arrived(id(t))
+        if b is not None:
+            self._flush_bucket(b)
+
+    def _flush_bucket(self, b):
+        """Everything bucket b needs has arrived: gather its gradients into the flat array, finish the weight-norm
+        chain rule for its convolutions and start its all-reduce while the backward goes on."""
+        st, work = self.state, self._bucket_work[b]
+        stream = torch.cuda.current_stream().cuda_stream
+        st.gather_grads(stream, work["slots"])
+        for lo, hi in work["rows"]:
+            st.weight_norm_bwd(stream, lo, hi)
+        self.bucket_log.append((b, sum(self._plan.pending)))
+        if self.world > 1:
+            lo, hi = work["range"]
+            self._works.append(dist.all_reduce(st.G[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
 
     def set_epoch(self, epoch):
         self.beta = kl_beta(epoch, self.hp.kl_warmup_epochs, self.hp.kl_warmup_smooth_start)
@@ -293,17 +433,32 @@ class Trainer:
         nll, kl, nelbo = self.model(x, True, eps, noise)
         global_batch = x.shape[0] * self.world                       # tr.py:174
         loss = (nll.sum() + self.beta_dev * kl.sum()) * (1.0 / global_batch)
+        if self._buckets:
+            self._plan.reset()
+            self._works, self.bucket_log = [], []
+            self._bucketing = True
+            try:
+                loss.backward()                                      # buckets flush from the gradient hooks
+            finally:
+                self._bucketing = False
+            for b in self._plan.remaining():                         # sources that received no gradient this step
+                self._flush_bucket(b)
+            return nll, kl
         loss.backward()
         st.gather_grads(stream)                                      # per-tensor gradients -> flat G / dW
         if st.wn_rows:                                               # dW -> grads of v and log_g
-            _lib.call("davi_weight_norm_bwd", st.P.data_ptr(), st.dW.data_ptr(), st.G.data_ptr(), rv.data_ptr(),
-                      rg.data_ptr(), rw.data_ptr(), rc.data_ptr(), st.wn_rows, stream)
+            st.weight_norm_bwd(stream)
         return nll, kl
 
     def all_reduce(self):
-        """The step's only collective: sum of all gradients (MirroredStrategy's
-        implicit all-reduce); one NCCL call on the flat gradient array."""
-        if self.world > 1:
+        """The step's only exchange: sum of all gradients (MirroredStrategy's implicit all-reduce).  Bucketed
+        path: the per-bucket NCCL calls were started during the backward, here they are joined; otherwise one
+        NCCL call on the flat gradient array."""
+        if self._buckets:
+            for w in self._works:
+                w.wait()
+            self._works = []
+        elif self.world > 1:
             dist.all_reduce(self.state.G, op=dist.ReduceOp.SUM)
 
     def _advance_hyper(self):

@@ -99,3 +99,42 @@ def test_fused_weight_norm_matches_per_layer_path(cuda, convs):
     assert torch.allclose(nll1, nll2, rtol=1e-5) and torch.allclose(kl1, kl2, rtol=1e-5)
     err = (g1 - g2).norm() / g2.norm()
     assert err < 1e-4, err.item()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_bucketed_gradient_exchange_equals_the_single_exchange(cuda, use_graph):
+    """The bucketed path (gradients gathered, weight-norm chain rule finished and the bucket's all-reduce started
+    from gradient hooks while the backward runs; run.py:94-95, tr.py:160-174) must leave the same flat gradient
+    array and parameters as the gather-everything-after-the-backward path -- here on one rank, i.e. without the
+    collective itself (tests/test_host_logic.py runs it across two gloo ranks)."""
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    from deep_attentive_vi_b200.util.trainer import Trainer
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    kw = parse_flags(**helpers.SMALL_CIFAR)
+    B = 4
+    xs = [helpers.synthetic_images(kw, B, seed=s).to(cuda) for s in range(4)]
+    results = []
+    for bucket_mb in (0, 0.1):
+        torch.manual_seed(0)
+        m = DeepVAE(**kw)
+        helpers.randomize_zero_init_scalars(m)
+        eps, noise = m.draw_noise(B, "cpu", generator=torch.Generator().manual_seed(1), training=True)
+        eps = [e.to(cuda) for e in eps]
+        noise = [None if nz is None else tuple(None if t is None else t.to(cuda) for t in nz) for nz in noise]
+        m = m.to(cuda)
+        m.draw_noise = lambda *a, **k: (eps, noise)
+        tr = Trainer(m, device=cuda, use_graph=use_graph, graph_warmup=2, bucket_mb=bucket_mb)
+        for x in xs:
+            tr.train_step(x)
+        if bucket_mb:
+            assert len(tr._plan.bounds) >= 3                      # several buckets at this size
+            if not use_graph:
+                # overlap: all but the last flushes happened while other buckets were still waiting for gradients
+                assert sum(1 for _, outstanding in tr.bucket_log if outstanding > 0) >= len(tr._plan.bounds) - 2
+                assert sorted(b for b, _ in tr.bucket_log) == list(range(len(tr._plan.bounds)))
+        results.append((tr.state.G.clone(), tr.state.P.clone()))
+    (g0, p0), (g1, p1) = results
+    # two runs of the SAME path differ in the last bits (atomic float sums in the scalar-gradient reductions)
+    assert (g0 - g1).abs().max().item() <= 1e-5 * g0.abs().max().item(), ((g0 - g1).abs().max().item(), g0.abs().max().item())
+    assert (p0 - p1).abs().max().item() < 1e-3

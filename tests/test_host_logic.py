@@ -167,3 +167,87 @@ def test_conv_precision_modes_are_validated():
     finally:
         ops.set_conv_precision("3xtf32")
     assert torch.backends.cudnn.allow_tf32 and not torch.backends.cuda.matmul.allow_tf32
+
+
+def test_gradient_bucket_plan():
+    """GradBuckets: buckets are contiguous, cover the flat array, never split a source's hull, and report
+    completion exactly once per bucket."""
+    from deep_attentive_vi_b200.util.trainer import GradBuckets
+    # a: plain parameter; b: conv kernel (v 100..400, log_g 400..410); c, d: parameters; e: conv with v / log_g apart
+    sources = {"a": [(0, 64)], "b": [(100, 400), (400, 410)], "c": [(448, 500)], "d": [(512, 900)],
+               "e": [(960, 1500), (1600, 1610)], "f": [(1520, 1580)]}
+    plan = GradBuckets(sources, 2048, 400)
+    assert plan.bounds[0][0] == 0 and plan.bounds[-1][1] == 2048
+    assert all(a[1] == b[0] for a, b in zip(plan.bounds, plan.bounds[1:]))
+    for k, ranges in sources.items():                              # every range of a source inside ITS bucket
+        lo, hi = plan.bounds[plan.bucket_of[k]]
+        assert all(lo <= r0 and r1 <= hi for r0, r1 in ranges), (k, plan.bounds)
+    assert plan.bucket_of["e"] == plan.bucket_of["f"]               # f lies inside e's hull: one atom
+    assert len(plan.bounds) >= 3
+    done = []
+    for k in ["f", "e", "d", "d", "c", "b"]:                        # reverse order of the flat layout, one repeat
+        b = plan.arrived(k)
+        if b is not None:
+            done.append(b)
+    assert done == sorted(set(done), reverse=True) and len(done) == len(set(done))
+    rest = plan.remaining()                                         # "a" never arrived: its bucket is flushed at the end
+    assert plan.bucket_of["a"] in rest and not (set(rest) & set(done))
+    assert sorted(rest + done) == list(range(len(plan.bounds)))
+    assert plan.remaining() == []
+    plan.reset()
+    assert plan.arrived("a") is not None or len(plan.members[plan.bucket_of["a"]]) > 1
+
+
+def _bucket_worker(rank, world, port, ret):
+    """The bucketed exchange across two gloo ranks: per-bucket async all-reduces started from gradient hooks
+    during the backward, joined afterwards, against ONE all-reduce of the flat gradient array."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deep_attentive_vi_b200.util.trainer import GradBuckets
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Linear(32, 32) for _ in range(6)]).double()
+    params = list(net.parameters())
+    offs, off = {}, 0
+    for p in params:
+        offs[id(p)] = (off, off + p.numel()); off += p.numel() + 8          # gaps, like the padded flat layout
+    flat = torch.zeros(off, dtype=torch.float64)
+    plan = GradBuckets({k: [r] for k, r in offs.items()}, off, 1500)
+    works, order = [], []
+
+    def arrived(p):
+        b = plan.arrived(id(p))
+        if b is None:
+            return
+        for k in plan.members[b]:
+            q = next(t for t in params if id(t) == k)
+            flat[offs[k][0]:offs[k][1]].copy_(q.grad.reshape(-1))
+        lo, hi = plan.bounds[b]
+        order.append(b)
+        works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    for p in params:
+        p.register_post_accumulate_grad_hook(arrived)
+    x = torch.randn(5, 32, dtype=torch.float64, generator=torch.Generator().manual_seed(10 + rank))
+    net(x).square().sum().backward()
+    assert plan.remaining() == []                                   # every bucket was flushed from a hook
+    for w in works:
+        w.wait()
+    want = torch.zeros_like(flat)
+    for p in params:
+        want[offs[id(p)][0]:offs[id(p)][1]].copy_(p.grad.reshape(-1))
+    dist.all_reduce(want, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ret["err"] = float((flat - want).abs().max())
+        ret["order"] = list(order)
+        ret["nb"] = len(plan.bounds)
+    dist.destroy_process_group()
+
+
+def test_bucketed_all_reduce_with_gloo():
+    world = 2
+    port = 29500 + (os.getpid() + 17) % 1000
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_bucket_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret["err"] == 0.0
+        assert ret["nb"] >= 3 and ret["order"] == sorted(ret["order"], reverse=True)   # last layers' buckets first
