@@ -389,8 +389,11 @@ def nl_roofline(shapes, device):
 # ---------------------------------------------------------------------------
 
 CONV_NOTE = {
-    "3xtf32": "cuDNN on TF32 tensor cores with 3xTF32 error compensation (fp32-grade: operands split hi/lo by "
-              "davi_split_tf32, three products accumulated in fp32 over a tripled contraction axis)",
+    "3xtf32": "own tcgen05 implicit-GEMM kernels (csrc/conv_tc.cu: CTA pairs, stream-K, 3xTF32 error compensation built in "
+              "shared memory / TMEM, fp32-grade) for stride-1 'same' convolutions; cuDNN TF32 with split operands over a "
+              "tripled contraction axis for the few shapes outside their envelope (stride 2, 138-channel pre-processor)",
+    "3xtf32-cudnn": "cuDNN on TF32 tensor cores with 3xTF32 error compensation (fp32-grade: operands split hi/lo by "
+                    "davi_split_tf32, three products accumulated in fp32 over a tripled contraction axis)",
     "fp32": "cuDNN fp32 (CUDA cores)",
     "tf32": "cuDNN plain TF32 (opt-in; operands truncated to 10 mantissa bits, below the reference's fp32)",
 }
@@ -470,7 +473,8 @@ def run_davi(args):
     def measure(convs, sampler=None, rooflines=False):
         """Whole train steps of the model with the host-side convolutions in precision `convs`
         (the hot-path kernels always compute in fp32): device-resident and end-to-end timings."""
-        ops.set_conv_precision(convs)
+        ops.set_conv_impl("cudnn" if convs == "3xtf32-cudnn" else "tcgen05")
+        ops.set_conv_precision("3xtf32" if convs == "3xtf32-cudnn" else convs)
         torch.manual_seed(0)
         model = M.DeepVAE(**M.parse_flags(**flags)).to(device)
         trainer = Trainer(model, device=device, world_size=world, rank=rank, use_graph=not args.eager,
@@ -724,7 +728,8 @@ def run_is_eval(args):
     from deep_attentive_vi_b200 import model as M
     from deep_attentive_vi_b200.util.eval import GraphedChunks, importance_log_likelihood
     world, rank, local, device = dist_setup()
-    ops.set_conv_precision(args.convs)
+    ops.set_conv_impl("cudnn" if args.convs == "3xtf32-cudnn" else "tcgen05")
+    ops.set_conv_precision("3xtf32" if args.convs == "3xtf32-cudnn" else args.convs)
     torch.manual_seed(0)                                      # same weights on every rank
     model = M.DeepVAE(**M.parse_flags(**M.CIFAR10_16L)).to(device).eval()
     B, K, chunk = 16, args.is_samples, 25
@@ -792,9 +797,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--no-full-batch-step", action="store_true",
                     help="reference arm: skip the one extra CPU step at the workload's full batch size")
-    ap.add_argument("--convs", default="3xtf32", choices=["3xtf32", "fp32", "tf32"],
+    ap.add_argument("--convs", default="3xtf32", choices=["3xtf32", "3xtf32-cudnn", "fp32", "tf32"],
                     help="precision of the host-side cuDNN convolutions (default: fp32-grade 3xTF32)")
-    ap.add_argument("--alt-convs", default="", choices=["", "3xtf32", "fp32", "tf32"],
+    ap.add_argument("--alt-convs", default="", choices=["", "3xtf32", "3xtf32-cudnn", "fp32", "tf32"],
                     help="second precision measured for the record into 'alt_convs' ('' = skip)")
     ap.add_argument("--fp32-convs", action="store_true", help="same as --convs fp32")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")

@@ -53,6 +53,11 @@ SIGNATURES = {
     "davi_multi_copy": (_i, [_pp, _lp, _lp, _i, _f, _s]),
     "davi_split_tf32": (_i, [_f, _f, _l, _i, _i, _i, _s]),
     "davi_split_tf32_dual": (_i, [_f, _f, _f, _l, _i, _i, _i, _s]),
+    "davi_conv2d_workspace_bytes": (_z, []),
+    "davi_conv2d_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "davi_conv2d_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _f, _z, _s]),
+    "davi_conv2d_wgrad": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _f, _z, _s]),
+    "davi_conv2d_wt": (_i, [_f, _f, _i, _i, _i, _s]),
     "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
     "davi_adamax_step_dev": (_i, [_f, _f, _f, _f, _l, _f, _r, _r, _r, _r, _s]),
 }

@@ -1058,6 +1058,34 @@ int make_tmap_rows(CUtensorMap* tm, const float* base, int inner, int rows, int 
     return DAVI_OK;
 }
 
+// General form (conv_tc.cu): `rank`-dimensional fp32 tensor, dims innermost first, byte strides of dims 1..rank-1,
+// box = [32 floats x ...]; swizzle: 0 = 128B (K-major operand tiles), 1 = 128B with 32-byte atoms (the MN-major
+// operand layout), 2 = none (rows read by threads).
+int make_tmap_nd(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int swizzle) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return DAVI_ECUDA;
+    }
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, b, e,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                  : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a rank-%d map, dims %llu %llu %llu, box %u %u %u", (int)r, rank,
+                  (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)(rank > 2 ? d[2] : 0), b[0], b[1],
+                  rank > 2 ? b[2] : 0);
+        return DAVI_ECUDA;
+    }
+    return DAVI_OK;
+}
+
 static bool pv_geom(int N, int d, int C, bool stats_in_smem, PvGeom& g) {
     if (N % kPvKB || N < kPvKB || d % 4 || d < 4 || d > 32 || C % 4 || C < 4 || C > 320) return false;
     g.N = N; g.d = d; g.C = C;

@@ -807,10 +807,107 @@ class _ConvBias3x(torch.autograd.Function):
         return gx, gw, gb, None, None
 
 
+# Implementation of the fp32-grade ("3xtf32") convolutions:
+#   "tcgen05" (default)  the repo's own implicit-GEMM kernels (csrc/conv_tc.cu: davi_conv2d_fwd / _wgrad) for every
+#                        shape inside their envelope (stride 1, 'same' padding, 16-byte-aligned channel counts);
+#                        the few others (stride-2 cells, the 138-channel pre-processor) go through cuDNN below
+#   "cudnn"              one cuDNN TF32 call per conv / dgrad / wgrad over a tripled contraction axis (_ConvBias3x)
+CONV_IMPLS = ("tcgen05", "cudnn")
+_conv_impl = "tcgen05"
+_conv_ws = {}          # device index -> zero-initialised workspace of the stream-K split (one per device: the
+                       # model's convolutions are issued on one stream at a time)
+
+
+def set_conv_impl(impl):
+    global _conv_impl
+    if impl not in CONV_IMPLS:
+        raise ValueError(f"conv implementation {impl!r}: expected one of {CONV_IMPLS}")
+    _conv_impl = impl
+
+
+def get_conv_impl():
+    return _conv_impl
+
+
+def _conv_workspace(dev):
+    ws = _conv_ws.get(dev.index)
+    if ws is None:
+        nbytes = _lib.load().davi_conv2d_workspace_bytes()
+        ws = _conv_ws[dev.index] = torch.zeros(nbytes // 4, device=dev, dtype=torch.float32)
+    return ws, ws.numel() * 4
+
+
+def _nhwc(t):
+    """NCHW-shaped tensor -> its [B,H,W,C] view, contiguous (a copy only if it was not channels_last)."""
+    v = t.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def conv_tc_supported(x, w, stride, padding):
+    s = (stride, stride) if isinstance(stride, int) else tuple(stride)
+    p = (padding, padding) if isinstance(padding, int) else tuple(padding)
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    if s != (1, 1) or p != ((kh - 1) // 2, (kw - 1) // 2):
+        return False
+    return bool(_lib.load().davi_conv2d_supported(B, H, W, Cin, Cout, kh, kw))
+
+
+def conv2d_tc_fwd(x, w, b):
+    """x [B,H,W,Cin] contiguous, w [Cout,kh,kw,Cin] contiguous (OHWI), b [Cout] or None -> y [B,H,W,Cout]."""
+    B, H, W, Cin = x.shape
+    Cout, kh, kw, _ = w.shape
+    y = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.float32)
+    ws, wsb = _conv_workspace(x.device)
+    _lib_call("davi_conv2d_fwd", _p(x), _p(w), _p(b) if b is not None else None, _p(y), B, H, W, Cin, Cout, kh, kw,
+              Cin, Cout, _p(ws), wsb, _stream())
+    return y
+
+
+def conv2d_tc_wgrad(x, gy, kh, kw):
+    """x [B,H,W,Cin], gy [B,H,W,Cout] contiguous -> gw [Cout,kh,kw,Cin]."""
+    B, H, W, Cin = x.shape
+    Cout = gy.shape[-1]
+    gw = torch.empty((Cout, kh, kw, Cin), device=x.device, dtype=torch.float32)
+    ws, wsb = _conv_workspace(x.device)
+    _lib_call("davi_conv2d_wgrad", _p(x), _p(gy), _p(gw), B, H, W, Cin, Cout, kh, kw, Cin, Cout, _p(ws), wsb, _stream())
+    return gw
+
+
+class _ConvTC(torch.autograd.Function):
+    """The convolution of the ResNet cells on the repo's tcgen05 kernels (fp32-grade, 3xTF32 compensation in shared
+    memory): forward, input gradient = the forward kernel on the transposed + flipped weights (davi_conv2d_wt),
+    weight gradient = davi_conv2d_wgrad, bias gradient = davi_colsum.  Saves x and w themselves -- no split copies."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xh, wh = _nhwc(x), _nhwc(w)
+        ctx.save_for_backward(xh, wh)
+        return conv2d_tc_fwd(xh, wh, b).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, wh = ctx.saved_tensors
+        gyh = _nhwc(gy)
+        Cout, kh, kw, Cin = wh.shape
+        gx = gw = gb = None
+        if ctx.needs_input_grad[2]:
+            gb = colsum_nhwc(gy)                                   # first: gy is still L2-resident
+        if ctx.needs_input_grad[0]:
+            wt = torch.empty((Cin, kh, kw, Cout), device=wh.device, dtype=torch.float32)
+            _lib_call("davi_conv2d_wt", _p(wh), _p(wt), Cout, kh * kw, Cin, _stream())
+            gx = conv2d_tc_fwd(gyh, wt, None).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            gw = conv2d_tc_wgrad(xh, gyh, kh, kw).permute(0, 3, 1, 2)
+        return gx, gw, gb
+
+
 def conv2d_bias(x, w, b, stride=1, padding=0):
     """F.conv2d(x, w, b) on NCHW views of channels_last tensors, with the fast bias gradient, in the
-    precision selected by set_conv_precision()."""
+    precision selected by set_conv_precision() (and, for "3xtf32", the implementation of set_conv_impl())."""
     _require_cuda(x, w, b)
+    if _conv_precision == "3xtf32" and _conv_impl == "tcgen05" and conv_tc_supported(x, w, stride, padding):
+        return _ConvTC.apply(x, w, b)
     if _conv_precision == "3xtf32":
         if not torch.backends.cudnn.allow_tf32:
             raise RuntimeError("conv precision '3xtf32' needs torch.backends.cudnn.allow_tf32 = True "

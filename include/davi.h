@@ -57,6 +57,7 @@ int davi_last_error(char* buf, size_t buf_bytes);
 #define DAVI_OPT_NONLOCAL_IMPL 1  /* 1: exact-fp32 CUDA-core nonlocal kernels instead of tcgen05 */
 #define DAVI_OPT_NL_DS 2          /* 1: per-block dQ/dK variant also for N = 256                */
 #define DAVI_OPT_NL_BWD 3         /* 1: nonlocal gradient as three launches instead of one      */
+#define DAVI_OPT_CONV_DEBUG 4      /* profiling only (WRONG results): bits: 1 no lo arithmetic, 2 one MMA of three, 4 no stores, 8 256+rest column split, 16 / 32 no A / B loads */
 #define DAVI_OPT_COUNT_ 8
 int davi_set_option(int option, int value);
 int davi_get_option(int option);
@@ -374,6 +375,38 @@ int davi_split_tf32(const float* src, float* dst, int64_t rows, int C, int layou
 /* Both layouts from one read: dst_ch = layout 0 with pattern_ch, dst_pl = layout 1 with pattern_pl. */
 int davi_split_tf32_dual(const float* src, float* dst_ch, float* dst_pl, int64_t rows, int C,
                          int pattern_ch, int pattern_pl, davi_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * 8(f1)  Dense convolution of the ResNet cells on the tensor cores.
+ * Replaces the tf.keras.layers.Conv2D calls behind WeightNorm
+ * (layers/resnet.py:589-601,613-633; layers/weight_norm.py:126-135) for
+ * stride 1, padding 'same', odd kernel sizes:
+ *     y[b,h,w,co] = bias[co] + sum_{r,s,ci} x[b, h+r-(kh-1)/2, w+s-(kw-1)/2, ci] * w[co,r,s,ci]
+ * x [B,H,W,Cin] pixel stride x_sp; y [B,H,W,Cout] pixel stride y_sp;
+ * w [Cout][kh][kw][Cin] dense (OHWI: the channels-last memory of a [Cout,Cin,kh,kw] kernel);
+ * bias [Cout] or NULL.  W in {8,16,32}, H*W % 256 == 0, Cin % 4 == Cout % 4 == 0, Cin, Cout <= 384.
+ * fp32-grade: implicit GEMM on tcgen05 (TF32 operands, fp32 accumulation in TMEM) with the
+ * 3xTF32 error compensation computed in shared memory (csrc/conv_tc.cu).
+ * workspace: davi_conv2d_workspace_bytes() bytes, ZERO-FILLED ONCE by the caller before its first
+ * use and then left alone (the kernel keeps partial accumulators and hand-shake flags of its
+ * stream-K split there and leaves the flags zero); one workspace per stream.
+ * Input gradient:  gx = davi_conv2d_fwd(gy, wt, NULL) with wt from davi_conv2d_wt and Cin/Cout swapped.
+ * Weight gradient: gw[co][r][s][ci] = sum_{b,h,w} gy[b,h,w,co] * x[b, h+r-(kh-1)/2, w+s-(kw-1)/2, ci],
+ * OVERWRITTEN.  (The bias gradient is davi_colsum of gy.)
+ * davi_conv2d_supported returns 1 when the shape is inside the kernel's envelope, else 0.
+ * ---------------------------------------------------------------------- */
+size_t davi_conv2d_workspace_bytes(void);
+int davi_conv2d_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw);
+int davi_conv2d_fwd(const float* x, const float* w, const float* bias, float* y,
+                    int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                    int64_t x_sp, int64_t y_sp, void* workspace, size_t workspace_bytes,
+                    davi_stream_t stream);
+int davi_conv2d_wgrad(const float* x, const float* gy, float* gw,
+                      int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                      int64_t x_sp, int64_t gy_sp, void* workspace, size_t workspace_bytes,
+                      davi_stream_t stream);
+/* wt[ci][taps-1-tap][co] = w[co][tap][ci] (taps = kh*kw): the weights of the input-gradient convolution */
+int davi_conv2d_wt(const float* w, float* wt, int Cout, int taps, int Cin, davi_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -128,6 +128,27 @@ def nonlocal_core(proj_query, proj_key, proj_value, inputs, gamma, scale=None):
 
 
 # ---------------------------------------------------------------------------
+# f1: the dense convolution of the ResNet cells
+# ---------------------------------------------------------------------------
+
+def conv2d_same(x, kernel, bias=None):
+    """tf.keras.layers.Conv2D(kernel_size=k, strides=1, padding='same') as the cells build it
+    (layers/resnet.py:589-601 behind WeightNorm, layers/weight_norm.py:126-135), written out tap by tap
+    (library semantics: cross-correlation, zero padding (k-1)//2 on each side for odd k).
+
+    x [B,H,W,Cin] NHWC, kernel [kh,kw,Cin,Cout] (the Keras HWIO layout), bias [Cout] -> [B,H,W,Cout]."""
+    B, H, W, _ = x.shape
+    kh, kw, _, cout = kernel.shape
+    pt, pl = (kh - 1) // 2, (kw - 1) // 2
+    xp = torch.nn.functional.pad(x, (0, 0, pl, kw - 1 - pl, pt, kh - 1 - pt))
+    y = x.new_zeros(B, H, W, cout)
+    for r in range(kh):
+        for s in range(kw):
+            y = y + torch.einsum("bhwi,io->bhwo", xp[:, r:r + H, s:s + W, :], kernel[r, s])
+    return y if bias is None else y + bias
+
+
+# ---------------------------------------------------------------------------
 # R5/R6: bounded residual Gaussians, sample, KL, log-probs
 # ---------------------------------------------------------------------------
 

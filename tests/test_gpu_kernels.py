@@ -362,6 +362,7 @@ def test_conv_3xtf32_is_fp32_grade(cuda, B, HW, ci, co, k, stride, pad):
     cuDNN's CUDA-core fp32 sits at ~1e-6, plain TF32 at ~5e-4."""
     from deep_attentive_vi_b200 import ops
     ops.set_conv_precision("3xtf32")
+    ops.set_conv_impl("cudnn")
     torch.manual_seed(ci + co)
     x = torch.randn(B, HW, HW, ci, device=cuda).permute(0, 3, 1, 2).requires_grad_()
     w = (torch.randn(co, ci, k, k, device=cuda) / (ci * k * k) ** 0.5).contiguous(
@@ -378,6 +379,69 @@ def test_conv_3xtf32_is_fp32_grade(cuda, B, HW, ci, co, k, stride, pad):
     for a, c, name in zip(g, gd, "x w b".split()):
         assert err(a, c) < 3e-5, (name, err(a, c))
     assert g[0].is_contiguous(memory_format=torch.channels_last) and g[1].is_contiguous(memory_format=torch.channels_last)
+    ops.set_conv_impl("tcgen05")
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,k", [
+    (2, 16, 16, 32, 32, 1),          # one chunk, no split
+    (2, 16, 16, 64, 48, 3),          # accumulator width that is not a multiple of 32 columns
+    (3, 16, 16, 276, 276, 3),        # ragged last channel chunk (276 = 8 * 32 + 20), two MMAs per k-step
+    (5, 16, 16, 20, 276, 1),         # fewer channels than one chunk
+    (2, 32, 32, 64, 64, 3),          # 32-wide maps: four tiles per image
+    (1, 32, 8, 36, 40, 3),           # 8-wide map: 16 image rows per CTA
+    (40, 16, 16, 276, 40, 3),        # the prior / posterior parameter heads
+    (40, 16, 16, 316, 316, 3),       # headline shapes at the bench batch: stream-K segments with hand-over flags
+    (40, 16, 16, 276, 340, 1),       # packed q|k|v projection of the nonlocal blocks (more than 320 columns)
+])
+def test_conv_tcgen05_matches_oracle(cuda, B, H, W, ci, co, k):
+    """davi_conv2d_fwd / davi_conv2d_wt / davi_conv2d_wgrad (csrc/conv_tc.cu, called through the C ABI by
+    ops.conv2d_bias) against oracle.ops.conv2d_same in float64 (res.py:589-601): output, input gradient, weight
+    gradient and bias gradient within 3e-5 of each tensor's max-abs (the bar of the 3xTF32 cuDNN path it
+    replaces; measured 4e-7 .. 1.2e-5, growing with the contraction length).  Every case runs twice: the
+    hand-over flags of the stream-K split must be left clean."""
+    from deep_attentive_vi_b200 import ops
+    from oracle import ops as R
+    ops.set_conv_precision("3xtf32")
+    ops.set_conv_impl("tcgen05")
+    torch.manual_seed(ci + co)
+    x = torch.randn(B, H, W, ci, device=cuda).permute(0, 3, 1, 2).requires_grad_()
+    w = (torch.randn(co, ci, k, k, device=cuda) / (ci * k * k) ** 0.5).contiguous(
+        memory_format=torch.channels_last).requires_grad_()
+    b = torch.randn(co, device=cuda, requires_grad=True)
+    assert ops.conv_tc_supported(x, w, 1, k // 2)
+    go = torch.randn(B, co, H, W, device=cuda).contiguous(memory_format=torch.channels_last)
+    xd = x.detach().permute(0, 2, 3, 1).double().cpu().requires_grad_()
+    wd = w.detach().permute(2, 3, 1, 0).double().cpu().requires_grad_()            # HWIO, like Keras
+    bd = b.detach().double().cpu().requires_grad_()
+    yd = R.conv2d_same(xd, wd, bd)
+    gd = torch.autograd.grad(yd, (xd, wd, bd), go.permute(0, 2, 3, 1).double().cpu())
+    err = lambda a, c: ((a.double().cpu() - c).abs().max() / c.abs().max()).item()
+    for _ in range(2):
+        y = ops.conv2d_bias(x, w, b, stride=1, padding=k // 2)
+        g = torch.autograd.grad(y, (x, w, b), go)
+        assert err(y.permute(0, 2, 3, 1), yd.detach()) < 3e-5
+        assert err(g[0].permute(0, 2, 3, 1), gd[0]) < 3e-5, ("x", err(g[0].permute(0, 2, 3, 1), gd[0]))
+        assert err(g[1].permute(2, 3, 1, 0), gd[1]) < 3e-5, ("w", err(g[1].permute(2, 3, 1, 0), gd[1]))
+        assert err(g[2], gd[2]) < 3e-5
+        assert g[0].is_contiguous(memory_format=torch.channels_last) and g[1].permute(0, 2, 3, 1).is_contiguous()
+    ws, _ = ops._conv_workspace(cuda)
+    assert int(ws[:256].view(torch.int32).abs().max()) == 0
+
+
+def test_conv_tcgen05_envelope_and_fallback(cuda):
+    """Shapes outside the kernel's envelope (stride 2, channel counts that are not 16-byte multiples, more than
+    512 output channels) go through the cuDNN 3xTF32 path and still meet the same bar."""
+    from deep_attentive_vi_b200 import ops
+    ops.set_conv_precision("3xtf32")
+    ops.set_conv_impl("tcgen05")
+    for (B, HW, ci, co, k, stride, pad) in ((4, 16, 40, 48, 3, 2, 1), (2, 32, 138, 138, 3, 1, 1), (2, 16, 276, 584, 1, 1, 0)):
+        torch.manual_seed(1)
+        x = torch.randn(B, HW, HW, ci, device=cuda).permute(0, 3, 1, 2)
+        w = (torch.randn(co, ci, k, k, device=cuda) / (ci * k * k) ** 0.5).contiguous(memory_format=torch.channels_last)
+        assert not ops.conv_tc_supported(x, w, stride, pad)
+        y = ops.conv2d_bias(x, w, None, stride=stride, padding=pad)
+        yd = torch.nn.functional.conv2d(x.double(), w.double(), None, stride=stride, padding=pad)
+        assert ((y.double() - yd).abs().max() / yd.abs().max()).item() < 3e-5
 
 
 def test_conv_bias_gradient_path_matches_autograd(cuda, fp32_convs):

@@ -177,3 +177,19 @@ def test_glue_matches_manual_composition():
     att = att + ref.gelu(ref.layer_norm(att, *c))
     nc2 = ctx + ref.gelu(ref.layer_norm(ctx, *a))
     assert torch.allclose(nc, nc2) and torch.allclose(pc, nc2 + 0.3 * att)
+
+
+def test_conv2d_same_restatement_matches_library_conv():
+    """oracle.ops.conv2d_same (tap-by-tap cross-correlation with 'same' zero padding, res.py:589-601) against
+    torch's convolution in float64, value and all gradients -- the checker of the tcgen05 convolution kernels."""
+    torch.manual_seed(0)
+    for k in (1, 3):
+        x = torch.randn(2, 8, 8, 5, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(k, k, 5, 7, dtype=torch.float64, requires_grad=True)
+        b = torch.randn(7, dtype=torch.float64, requires_grad=True)
+        y = ref.conv2d_same(x, w, b)
+        yl = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=k // 2).permute(0, 2, 3, 1)
+        assert torch.allclose(y, yl, atol=1e-12)
+        go = torch.randn_like(y)
+        for a, c in zip(torch.autograd.grad(y, (x, w, b), go), torch.autograd.grad(yl, (x, w, b), go)):
+            assert torch.allclose(a, c, atol=1e-12)
