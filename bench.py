@@ -217,13 +217,13 @@ def dw_roofline_of_step(trainer, x, device):
     from deep_attentive_vi_b200 import _lib, ops
     trainer._step_body(x)                                   # eager warm-up of this code path
     torch.cuda.synchronize()
-    ops.dw_trace, _lib.timed = [], {"prefix": "davi_dw_attn", "events": []}
+    ops.dw_trace, ops.conv_trace, _lib.timed = [], [], {"prefix": "davi_dw_attn", "events": []}
     try:
         trainer._step_body(x)
         torch.cuda.synchronize()
-        trace, events = ops.dw_trace, _lib.timed["events"]
+        trace, conv_trace, events = ops.dw_trace, ops.conv_trace, _lib.timed["events"]
     finally:
-        ops.dw_trace, _lib.timed = None, None
+        ops.dw_trace, ops.conv_trace, _lib.timed = None, None, None
     in_step_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in events)
     by_name = {}
     for name, e0, e1 in events:
@@ -251,7 +251,7 @@ def dw_roofline_of_step(trainer, x, device):
     moved = sum(dw_replay.moved_bytes(e) for e in trace)
     tb, tt, per = dw_replay.replay_roofline(trace, device)
     assert tb == alg
-    return {"trace": trace, "launches": len(trace), "algorithmic_bytes": alg, "moved_bytes": moved,
+    return {"trace": trace, "conv_trace": conv_trace, "launches": len(trace), "algorithmic_bytes": alg, "moved_bytes": moved,
             "in_step_ms": in_step_ms, "in_step_ms_by_entry_point": by_name, "in_step_kernel_ms": kern_ms,
             "in_step_kernels": kern_by_name, "stand_alone_ms": tt, "per_launch": per}
 
@@ -318,6 +318,57 @@ def elbo_roofline(batch, device):
         t = rot(make, nbytes)
         out[name] = {"us": round(t * 1e3, 2), "MB": round(nbytes / 1e6, 2), "GBs": round(nbytes / t / 1e6)}
     return out
+
+
+def conv_roofline(trace, device):
+    """Tensor-pipe view of the model's own convolution launches (`trace`: one (kind, B, H, W, Cin, Cout, kh, kw) per
+    davi_conv2d_fwd / davi_conv2d_wgrad call of a step, recorded by ops.conv_trace; the input gradient is a "fwd"
+    call with the channel counts swapped).  Algorithmic flops 2 B H W Cin Cout kh kw per call over the CUDA-event time
+    of the C-ABI calls, each distinct shape launched back to back on rotating operand sets whose footprint exceeds
+    L2.  The kernels execute 3 tcgen05 TF32 MMAs per algorithmic product (3xTF32)."""
+    import collections
+    import torch
+    from deep_attentive_vi_b200 import _lib
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    wsb = lib.davi_conv2d_workspace_bytes()
+    ws = torch.zeros(wsb // 4, device=device)
+    tot_f = tot_t = 0.0
+    per_shape = []
+    for (kind, B, H, W, Cin, Cout, kh, kw), count in sorted(collections.Counter(trace).items()):
+        per_set = 4 * B * H * W * (Cin + Cout)
+        sets = max(2, min(12, int(1.5 * 126e6 // per_set) + 1))
+        x = [torch.randn(B, H, W, Cin, device=device) for _ in range(sets)]
+        y = [torch.randn(B, H, W, Cout, device=device) for _ in range(sets)]
+        w = torch.randn(Cout, kh, kw, Cin, device=device) * 0.05
+        b = torch.randn(Cout, device=device)
+
+        def run(i):
+            if kind == "fwd":
+                _lib.call("davi_conv2d_fwd", x[i].data_ptr(), w.data_ptr(), b.data_ptr(), y[i].data_ptr(), B, H, W, Cin,
+                          Cout, kh, kw, Cin, Cout, ws.data_ptr(), wsb, stream)
+            else:
+                _lib.call("davi_conv2d_wgrad", x[i].data_ptr(), y[i].data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, kh, kw,
+                          Cin, Cout, ws.data_ptr(), wsb, stream)
+
+        for i in range(min(sets, 3)):
+            run(i)
+        torch.cuda.synchronize()
+        reps = max(sets, 8)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            run(i % sets)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        fl = 2.0 * B * H * W * Cin * Cout * kh * kw
+        tot_f += fl * count
+        tot_t += us * count
+        per_shape.append({"k": kind, "B": B, "HW": [H, W], "Cin": Cin, "Cout": Cout, "ks": [kh, kw], "calls": count,
+                          "us": round(us, 1), "TFLOPs": round(fl / us * 1e-6, 1)})
+        del x, y
+    return tot_f, tot_t / 1e3, per_shape
 
 
 def nl_roofline(shapes, device):
@@ -603,6 +654,18 @@ def run_davi(args):
                         "(3xTF32 error compensation, fp32-grade), so the tensor pipe runs at executed_frac",
                 "kernel_ms_per_step": tt_nl, "per_shape": per_shape}
             line["roofline_elbo"] = {"bound": "hbm", "peak": peak, "unit": "GB/s", "kernels": elbo_roofline(B, device)}
+            if dw.get("conv_trace"):
+                cf, ct, cper = conv_roofline(dw["conv_trace"], device)
+                ach_c = cf / ct / 1e9
+                line["roofline_conv"] = {
+                    "bound": "tensor", "kernel": f"convolutions on the own tcgen05 kernels: {len(dw['conv_trace'])} launches of one "
+                                                 "step (forward, input gradient, weight gradient), conv_gemm_kernel<0/1>",
+                    "achieved": ach_c, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach_c / tf32_peak,
+                    "executed_frac": 3 * ach_c / tf32_peak, "executed_frac_of_nominal_1125": 3 * ach_c / 1125.0,
+                    "peak_source": tf32_src, "kernel_ms_per_step": ct,
+                    "ncu": "profiles/r02_ncu_conv_tc_summary.txt: tcgen05 TF32 op rate 57-59 % of the SM's 4096 ops/clk "
+                           "(sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32 pct_of_peak_sustained_elapsed)",
+                    "per_shape": sorted(cper, key=lambda e: -e["us"] * e["calls"])[:14]}
         if world == 1 and not args.no_cpu_baseline:
             # median of >= 5 steps after 2 warm-ups, all host threads, bounded to --ref-batch images
             cores = os.cpu_count() or 1

@@ -356,29 +356,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
                     continue;
                 }
-                // every load of this column group goes out before the first use: bias, first contribution, accumulator
-                // the first contribution of this column group was requested one group ahead (wn); the next group's goes
-                // out now, before anything of this group is used
-                float4 w[8];
+                // the first contribution of this column group was requested one group ahead (wn), the second one (a tile cut
+                // into three segments: the usual case at 74 pairs for 40 tiles) and the next group's first go out now,
+                // before anything of this group is used: one L2 round trip per group instead of one per contribution
+                float4 w2[8];
                 const float4* part = part1 + (size_t)(c0 / 4) * 128;
+                if (ncontrib > 1) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) w2[q] = __ldcg(part + (size_t)2 * ncol4 * 128 + q * 128);
+                }
+                tmem_ld_wait();
                 if (ncontrib > 0) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) w[q] = wn[q];
+                    for (int q = 0; q < 8; ++q) {
+                        v[4 * q] += wn[q].x; v[4 * q + 1] += wn[q].y; v[4 * q + 2] += wn[q].z; v[4 * q + 3] += wn[q].w;
+                    }
                     if (c0 + 64 < g.n_total) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) wn[q] = __ldcg(part + 16 * 128 + q * 128);
                     }
                 }
-                tmem_ld_wait();
-                for (int p = 1; p <= ncontrib; ++p) {
+                for (int p = 2; p <= ncontrib; ++p) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        v[4 * q] += w[q].x; v[4 * q + 1] += w[q].y; v[4 * q + 2] += w[q].z; v[4 * q + 3] += w[q].w;
+                        v[4 * q] += w2[q].x; v[4 * q + 1] += w2[q].y; v[4 * q + 2] += w2[q].z; v[4 * q + 3] += w2[q].w;
                     }
-                    if (p < ncontrib) {
-                        part += (size_t)2 * ncol4 * 128;                   // (rare: a tile cut into three segments)
+                    if (p < ncontrib) {                                    // (a tile cut into more than three segments)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) w[q] = __ldcg(part + q * 128);
+                        for (int q = 0; q < 8; ++q) w2[q] = __ldcg(part + (size_t)2 * ncol4 * 128 * p + q * 128);
                     }
                 }
                 if (MODE == 0 && last_seg) {
@@ -905,6 +910,12 @@ extern "C" int davi_cv_trace_read(unsigned long long* out) {
 #endif
 
 extern "C" size_t davi_conv2d_workspace_bytes(void) { return conv_tc_workspace_bytes(); }
+
+extern "C" int davi_fill_zero(float* dst, int64_t n, davi_stream_t stream) {
+    DAVI_REQUIRE(dst && n >= 0, "null pointer / negative size");
+    DAVI_CUDA(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(float), (cudaStream_t)stream));
+    return DAVI_OK;
+}
 
 extern "C" int davi_conv2d_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw) {
     return conv_tc_supported(B, H, W, Cin, Cout, kh, kw) ? 1 : 0;

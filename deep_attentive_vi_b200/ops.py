@@ -814,6 +814,7 @@ class _ConvBias3x(torch.autograd.Function):
 #   "cudnn"              one cuDNN TF32 call per conv / dgrad / wgrad over a tripled contraction axis (_ConvBias3x)
 CONV_IMPLS = ("tcgen05", "cudnn")
 _conv_impl = "tcgen05"
+conv_trace = None      # measurement hook (bench.py): a list collects ("fwd" | "wgrad", B, H, W, Cin, Cout, kh, kw) per launch
 _conv_ws = {}          # device index -> zero-initialised workspace of the stream-K split (one per device: the
                        # model's convolutions are issued on one stream at a time)
 
@@ -843,14 +844,19 @@ def _nhwc(t):
     return v if v.is_contiguous() else v.contiguous()
 
 
-def conv_tc_supported(x, w, stride, padding):
+def _conv_tc_shape_ok(B, H, W, Cin, Cout, kh, kw, stride, padding):
     s = (stride, stride) if isinstance(stride, int) else tuple(stride)
     p = (padding, padding) if isinstance(padding, int) else tuple(padding)
-    B, Cin, H, W = x.shape
-    Cout, _, kh, kw = w.shape
     if s != (1, 1) or p != ((kh - 1) // 2, (kw - 1) // 2):
         return False
     return bool(_lib.load().davi_conv2d_supported(B, H, W, Cin, Cout, kh, kw))
+
+
+def conv_tc_supported(x, w, stride, padding):
+    """True when F.conv2d(x, w, stride, padding) (NCHW shapes) lies inside the envelope of the tcgen05 kernels."""
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    return _conv_tc_shape_ok(B, H, W, Cin, Cout, kh, kw, stride, padding)
 
 
 def conv2d_tc_fwd(x, w, b):
@@ -859,6 +865,8 @@ def conv2d_tc_fwd(x, w, b):
     Cout, kh, kw, _ = w.shape
     y = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.float32)
     ws, wsb = _conv_workspace(x.device)
+    if conv_trace is not None:
+        conv_trace.append(("fwd", B, H, W, Cin, Cout, kh, kw))
     _lib_call("davi_conv2d_fwd", _p(x), _p(w), _p(b) if b is not None else None, _p(y), B, H, W, Cin, Cout, kh, kw,
               Cin, Cout, _p(ws), wsb, _stream())
     return y
@@ -870,6 +878,8 @@ def conv2d_tc_wgrad(x, gy, kh, kw):
     Cout = gy.shape[-1]
     gw = torch.empty((Cout, kh, kw, Cin), device=x.device, dtype=torch.float32)
     ws, wsb = _conv_workspace(x.device)
+    if conv_trace is not None:
+        conv_trace.append(("wgrad", B, H, W, Cin, Cout, kh, kw))
     _lib_call("davi_conv2d_wgrad", _p(x), _p(gy), _p(gw), B, H, W, Cin, Cout, kh, kw, Cin, Cout, _p(ws), wsb, _stream())
     return gw
 
@@ -906,8 +916,20 @@ def conv2d_bias(x, w, b, stride=1, padding=0):
     """F.conv2d(x, w, b) on NCHW views of channels_last tensors, with the fast bias gradient, in the
     precision selected by set_conv_precision() (and, for "3xtf32", the implementation of set_conv_impl())."""
     _require_cuda(x, w, b)
-    if _conv_precision == "3xtf32" and _conv_impl == "tcgen05" and conv_tc_supported(x, w, stride, padding):
-        return _ConvTC.apply(x, w, b)
+    if _conv_precision == "3xtf32" and _conv_impl == "tcgen05":
+        if conv_tc_supported(x, w, stride, padding):
+            return _ConvTC.apply(x, w, b)
+        # channel counts that are not 16-byte multiples (the 138-channel pre/post-processing cells, the 3-channel
+        # stem, the 50-channel output head): zero-pad the channel axes, run the same kernels, slice the result
+        # (autograd turns the pads into slices and the slice into a pad on the way back)
+        pi, po = (-x.shape[1]) % 4, (-w.shape[0]) % 4
+        if (pi or po) and _conv_tc_shape_ok(x.shape[0], x.shape[2], x.shape[3], x.shape[1] + pi, w.shape[0] + po,
+                                            w.shape[2], w.shape[3], stride, padding):
+            F = torch.nn.functional
+            xp = F.pad(x.permute(0, 2, 3, 1), (0, pi)).permute(0, 3, 1, 2)
+            wp = F.pad(w.permute(0, 2, 3, 1), (0, pi, 0, 0, 0, 0, 0, po)).permute(0, 3, 1, 2)
+            bp = None if b is None else F.pad(b, (0, po))
+            return _ConvTC.apply(xp, wp, bp)[:, :w.shape[0]]
     if _conv_precision == "3xtf32":
         if not torch.backends.cudnn.allow_tf32:
             raise RuntimeError("conv precision '3xtf32' needs torch.backends.cudnn.allow_tf32 = True "

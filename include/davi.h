@@ -396,6 +396,8 @@ int davi_split_tf32_dual(const float* src, float* dst_ch, float* dst_pl, int64_t
  * davi_conv2d_supported returns 1 when the shape is inside the kernel's envelope, else 0.
  * ---------------------------------------------------------------------- */
 size_t davi_conv2d_workspace_bytes(void);
+/* dst[0 : n] = 0 on `stream` (the one-time zero fill of the workspace for callers without a memset of their own) */
+int davi_fill_zero(float* dst, int64_t n, davi_stream_t stream);
 int davi_conv2d_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw);
 int davi_conv2d_fwd(const float* x, const float* w, const float* bias, float* y,
                     int B, int H, int W, int Cin, int Cout, int kh, int kw,

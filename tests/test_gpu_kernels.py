@@ -429,19 +429,32 @@ def test_conv_tcgen05_matches_oracle(cuda, B, H, W, ci, co, k):
 
 
 def test_conv_tcgen05_envelope_and_fallback(cuda):
-    """Shapes outside the kernel's envelope (stride 2, channel counts that are not 16-byte multiples, more than
-    512 output channels) go through the cuDNN 3xTF32 path and still meet the same bar."""
-    from deep_attentive_vi_b200 import ops
+    """Shapes outside the kernel's envelope: stride 2 and more than 384 channels go through the cuDNN 3xTF32 path;
+    channel counts that are not 16-byte multiples (138-channel cells, 3-channel stem, 50-channel head) are zero-padded
+    onto the tcgen05 kernels.  All meet the same bar, output and gradients."""
+    from deep_attentive_vi_b200 import ops, _lib
     ops.set_conv_precision("3xtf32")
     ops.set_conv_impl("tcgen05")
-    for (B, HW, ci, co, k, stride, pad) in ((4, 16, 40, 48, 3, 2, 1), (2, 32, 138, 138, 3, 1, 1), (2, 16, 276, 584, 1, 1, 0)):
+    for (B, HW, ci, co, k, stride, pad, own) in ((4, 16, 40, 48, 3, 2, 1, False), (2, 16, 276, 584, 1, 1, 0, False),
+                                                 (2, 32, 138, 138, 3, 1, 1, True), (2, 32, 3, 138, 3, 1, 1, True),
+                                                 (2, 32, 138, 50, 3, 1, 1, True)):
         torch.manual_seed(1)
-        x = torch.randn(B, HW, HW, ci, device=cuda).permute(0, 3, 1, 2)
-        w = (torch.randn(co, ci, k, k, device=cuda) / (ci * k * k) ** 0.5).contiguous(memory_format=torch.channels_last)
+        x = torch.randn(B, HW, HW, ci, device=cuda).permute(0, 3, 1, 2).requires_grad_()
+        w = (torch.randn(co, ci, k, k, device=cuda) / (ci * k * k) ** 0.5).contiguous(
+            memory_format=torch.channels_last).requires_grad_()
+        b = torch.randn(co, device=cuda, requires_grad=True)
         assert not ops.conv_tc_supported(x, w, stride, pad)
-        y = ops.conv2d_bias(x, w, None, stride=stride, padding=pad)
-        yd = torch.nn.functional.conv2d(x.double(), w.double(), None, stride=stride, padding=pad)
-        assert ((y.double() - yd).abs().max() / yd.abs().max()).item() < 3e-5
+        n0 = _lib.launch_count()
+        y = ops.conv2d_bias(x, w, b, stride=stride, padding=pad)
+        go = torch.randn_like(y)
+        g = torch.autograd.grad(y, (x, w, b), go)
+        xd, wd, bd = [t.detach().double().requires_grad_() for t in (x, w, b)]
+        yd = torch.nn.functional.conv2d(xd, wd, bd, stride=stride, padding=pad)
+        gd = torch.autograd.grad(yd, (xd, wd, bd), go.double())
+        err = lambda a, c: ((a.double() - c).abs().max() / c.abs().max()).item()
+        assert err(y, yd) < 3e-5
+        for a, c, name in zip(g, gd, "x w b".split()):
+            assert a.shape == c.shape and err(a, c) < 3e-5, (name, err(a, c))
 
 
 def test_conv_bias_gradient_path_matches_autograd(cuda, fp32_convs):

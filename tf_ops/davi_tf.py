@@ -79,6 +79,13 @@ def _register_gradients():
         return _mod.davi_ln_gelu_grad(x=x, gamma=gamma, beta=beta, dy=dy, mode=op.get_attr("mode"),
                                       epsilon=op.get_attr("epsilon"))
 
+    @tf_ops.RegisterGradient("DaviConv2d")
+    def _conv2d_grad(op, dy):
+        x, w, _b = op.inputs
+        dx = _mod.davi_conv2d_input_grad(dy=dy, kernel_ohwi=w)
+        dw = _mod.davi_conv2d_filter_grad(x=x, dy=dy, kh=int(w.shape[1]), kw=int(w.shape[2]))
+        return dx, dw, tf.reduce_sum(dy, axis=[0, 1, 2])
+
     @tf_ops.RegisterGradient("DaviLnGeluRes")
     def _ln_gelu_res_grad(op, dy):
         x, gamma, beta, base, res_gamma = op.inputs

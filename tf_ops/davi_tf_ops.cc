@@ -521,3 +521,124 @@ class DaviSplitTf32Op : public OpKernel {
   int layout_, pattern_;
 };
 REGISTER_KERNEL_BUILDER(Name("DaviSplitTf32").Device(tf::DEVICE_GPU), DaviSplitTf32Op);
+
+// ---------------------------------------------------------------------------
+// DaviConv2d / DaviConv2dInputGrad / DaviConv2dFilterGrad: the Conv2D of the ResNet cells on the tcgen05 kernels
+// (row f1; src/layers/resnet.py:589-601,613-633, src/layers/weight_norm.py:126-135)
+//   x [B,H,W,Cin], kernel_ohwi [Cout,kh,kw,Cin] (tf.transpose(kernel_hwio, [3,0,1,2])), bias [Cout] -> [B,H,W,Cout]
+// stride 1, padding 'same'.  The stream-K workspace is a persistent buffer of the kernel object, zero-filled once.
+// ---------------------------------------------------------------------------
+namespace {
+class ConvWorkspace {
+ public:
+  tf::Status Get(OpKernelContext* ctx, void** ptr, size_t* bytes) {
+    *bytes = davi_conv2d_workspace_bytes();
+    if (!ready_) {
+      TF_RETURN_IF_ERROR(ctx->allocate_temp(tf::DT_FLOAT, TensorShape({(tf::int64)(*bytes / 4)}), &ws_));
+      TF_RETURN_IF_ERROR(Check(davi_fill_zero(P(&ws_), *bytes / 4, StreamOf(ctx)), "davi_fill_zero"));
+      ready_ = true;
+    }
+    *ptr = P(&ws_);
+    return tf::Status::OK();
+  }
+ private:
+  Tensor ws_;            // kept alive by the op kernel: the hand-shake flags inside must survive between calls
+  bool ready_ = false;
+};
+}  // namespace
+
+REGISTER_OP("DaviConv2d")
+    .Input("x: float").Input("kernel_ohwi: float").Input("bias: float")
+    .Output("y: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->UnknownShape());
+      return tf::Status::OK();
+    });
+
+class DaviConv2dOp : public OpKernel {
+ public:
+  explicit DaviConv2dOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& x = ctx->input(0);
+    const Tensor& w = ctx->input(1);
+    const Tensor& b = ctx->input(2);
+    OP_REQUIRES(ctx, x.dims() == 4 && w.dims() == 4 && w.dim_size(3) == x.dim_size(3),
+                tf::errors::InvalidArgument("DaviConv2d: x [B,H,W,Cin], kernel [Cout,kh,kw,Cin]"));
+    const int B = x.dim_size(0), H = x.dim_size(1), W = x.dim_size(2), Cin = x.dim_size(3);
+    const int Cout = w.dim_size(0), kh = w.dim_size(1), kw = w.dim_size(2);
+    Tensor* y;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B, H, W, Cout}), &y));
+    void* ws; size_t wsb;
+    OP_REQUIRES_OK(ctx, ws_.Get(ctx, &ws, &wsb));
+    OP_REQUIRES_OK(ctx, Check(davi_conv2d_fwd(P(x), P(w), b.NumElements() ? P(b) : nullptr, P(y), B, H, W, Cin, Cout,
+                                              kh, kw, Cin, Cout, ws, wsb, StreamOf(ctx)), "davi_conv2d_fwd"));
+  }
+ private:
+  ConvWorkspace ws_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviConv2d").Device(tf::DEVICE_GPU), DaviConv2dOp);
+
+REGISTER_OP("DaviConv2dInputGrad")
+    .Input("dy: float").Input("kernel_ohwi: float")
+    .Output("dx: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->UnknownShape());
+      return tf::Status::OK();
+    });
+
+class DaviConv2dInputGradOp : public OpKernel {
+ public:
+  explicit DaviConv2dInputGradOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& dy = ctx->input(0);
+    const Tensor& w = ctx->input(1);
+    const int B = dy.dim_size(0), H = dy.dim_size(1), W = dy.dim_size(2), Cout = dy.dim_size(3);
+    const int kh = w.dim_size(1), kw = w.dim_size(2), Cin = w.dim_size(3);
+    OP_REQUIRES(ctx, w.dim_size(0) == Cout, tf::errors::InvalidArgument("DaviConv2dInputGrad: channel mismatch"));
+    Tensor wt;
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, TensorShape({Cin, kh, kw, Cout}), &wt));
+    OP_REQUIRES_OK(ctx, Check(davi_conv2d_wt(P(w), P(&wt), Cout, kh * kw, Cin, StreamOf(ctx)), "davi_conv2d_wt"));
+    Tensor* dx;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B, H, W, Cin}), &dx));
+    void* ws; size_t wsb;
+    OP_REQUIRES_OK(ctx, ws_.Get(ctx, &ws, &wsb));
+    // the input gradient of a stride-1 'same' convolution = the forward kernel on the transposed + flipped weights
+    OP_REQUIRES_OK(ctx, Check(davi_conv2d_fwd(P(dy), P(&wt), nullptr, P(dx), B, H, W, Cout, Cin, kh, kw, Cout, Cin, ws,
+                                              wsb, StreamOf(ctx)), "davi_conv2d_fwd(input gradient)"));
+  }
+ private:
+  ConvWorkspace ws_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviConv2dInputGrad").Device(tf::DEVICE_GPU), DaviConv2dInputGradOp);
+
+REGISTER_OP("DaviConv2dFilterGrad")
+    .Input("x: float").Input("dy: float")
+    .Attr("kh: int").Attr("kw: int")
+    .Output("dkernel_ohwi: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->UnknownShape());
+      return tf::Status::OK();
+    });
+
+class DaviConv2dFilterGradOp : public OpKernel {
+ public:
+  explicit DaviConv2dFilterGradOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("kh", &kh_));
+    OP_REQUIRES_OK(c, c->GetAttr("kw", &kw_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& x = ctx->input(0);
+    const Tensor& dy = ctx->input(1);
+    const int B = x.dim_size(0), H = x.dim_size(1), W = x.dim_size(2), Cin = x.dim_size(3), Cout = dy.dim_size(3);
+    Tensor* dw;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({Cout, kh_, kw_, Cin}), &dw));
+    void* ws; size_t wsb;
+    OP_REQUIRES_OK(ctx, ws_.Get(ctx, &ws, &wsb));
+    OP_REQUIRES_OK(ctx, Check(davi_conv2d_wgrad(P(x), P(dy), P(dw), B, H, W, Cin, Cout, kh_, kw_, Cin, Cout, ws, wsb,
+                                                StreamOf(ctx)), "davi_conv2d_wgrad"));
+  }
+ private:
+  int kh_, kw_;
+  ConvWorkspace ws_;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviConv2dFilterGrad").Device(tf::DEVICE_GPU), DaviConv2dFilterGradOp);
