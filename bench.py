@@ -215,6 +215,16 @@ def dw_roofline_of_step(trainer, x, device):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import dw_replay
     from deep_attentive_vi_b200 import _lib, ops
+    # Rank 0 runs these eager steps ALONE: no collective may be issued (the bucketed gradient exchange starts its
+    # all-reduces from gradient hooks inside _step_body when world > 1 -- the other ranks are not here to answer)
+    world_saved, trainer.world = trainer.world, 1
+    try:
+        return _dw_roofline_of_step(trainer, x, device, torch, dw_replay, _lib, ops)
+    finally:
+        trainer.world = world_saved
+
+
+def _dw_roofline_of_step(trainer, x, device, torch, dw_replay, _lib, ops):
     trainer._step_body(x)                                   # eager warm-up of this code path
     torch.cuda.synchronize()
     ops.dw_trace, ops.conv_trace, _lib.timed = [], [], {"prefix": "davi_dw_attn", "events": []}
