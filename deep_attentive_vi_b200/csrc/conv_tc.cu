@@ -96,6 +96,8 @@ struct CvGeom {
 };
 
 struct CvArgs {
+    int act;                    // 1: the input goes through swish on its way into the tensor core (conv(swish(x)),
+                                //    layers/resnet.py:624-627); selects the ACT = 1 instance of the kernel
     const float* bias;          // MODE 0, nullable
     float* out;                 // MODE 0: [pixels, Cout];  MODE 1: gw [Cout][taps][Cin]
     uint32_t* flags;            // workspace header
@@ -220,6 +222,7 @@ __device__ __forceinline__ void cv_flag_wait(const uint32_t* f) {
     }
 }
 
+__device__ __forceinline__ float cv_swish(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 // ---- stream-K bookkeeping: every role of both CTAs walks the same list -------------------------------
 struct CvSeg {
     int tile, k0, k1;
@@ -252,7 +255,7 @@ struct CvWalk {
     }
 };
 
-template <int MODE>
+template <int MODE, int ACT>
 // (14 warps: 4 + 4 + 3 + 3 per SM sub-partition of 16 K registers -> at most 128 registers per thread)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -430,6 +433,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (MODE == 0 && last_seg) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");                 // the tile is complete in shared memory
+                // flat float4 index over the [128 x Cout] tile: consecutive threads write consecutive 16-byte pieces.
+                // (Fusing the block's shortcut or the activation gradient in here was measured and dropped: one CTA per
+                // SM has too few loads in flight -- +20 us per launch against 6-7 us for a separate elementwise kernel.)
                 const int C4 = g.Cout >> 2, total = 128 * C4;
                 const float* tile_s = reinterpret_cast<const float*>(smem);
                 float* out0 = a.out + ((int64_t)sg.tile * 256 + rank * 128) * g.out_sp;
@@ -489,6 +495,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const float* col = reinterpret_cast<const float*>(sA(s) + (lt >> 5) * 4096) + (lt & 31);
 #pragma unroll
                         for (int k = 0; k < 32; ++k) hi[k] = col[k * 32];
+                    }
+                    if (ACT) {                                             // swish(0) = 0: the zero padding stays zero
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) hi[k] = cv_swish(hi[k]);
                     }
                     if (!(g.debug & 1)) {
 #pragma unroll
@@ -805,8 +815,13 @@ static int cv_launch(const char* fn, const CUtensorMap& tmA, const CUtensorMap& 
     a.flags = reinterpret_cast<uint32_t*>(workspace);
     a.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCvFlagBytes);
     const size_t smem = 1024 + (size_t)g.stages * (kCvABytes + g.nb * 128) + (size_t)g.slots * g.nb * 128 + kCvStageBytes;
-    DAVI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_gemm_kernel<MODE><<<2 * g.pairs, kCvThreads, smem, st>>>(tmA, tmB, tmB1, a, g);
+    if (a.act) {
+        DAVI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_gemm_kernel<MODE, 1><<<2 * g.pairs, kCvThreads, smem, st>>>(tmA, tmB, tmB1, a, g);
+    } else {
+        DAVI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_gemm_kernel<MODE, 0><<<2 * g.pairs, kCvThreads, smem, st>>>(tmA, tmB, tmB1, a, g);
+    }
     int rc = check_launch(fn);
     if (rc || !g.reduce) return rc;
     conv_reduce_kernel<MODE><<<dim3(2 * g.tiles, (g.n_total + 31) / 32 * 8), 128, 0, st>>>(a, g);
@@ -814,8 +829,8 @@ static int cv_launch(const char* fn, const CUtensorMap& tmA, const CUtensorMap& 
 }
 
 int conv_fwd_tc_launch(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
-                       int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st) {
+                       int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, int act, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
     CvGeom g{};
     const int sms = cv_sms();
     if (!cv_common(g, B, H, W, Cin, Cout, kh, kw) || sms < 2) {
@@ -853,11 +868,12 @@ int conv_fwd_tc_launch(const float* x, const float* w, const float* bias, float*
     }
     CvArgs a{};
     a.bias = bias; a.out = y;
+    a.act = act;
     return cv_launch<0>("davi_conv2d_fwd", tmA, tmB, tmB1, a, g, workspace, workspace_bytes, st);
 }
 
 int conv_wgrad_tc_launch(const float* x, const float* gy, float* gw, int B, int H, int W, int Cin, int Cout, int kh,
-                         int kw, int64_t x_sp, int64_t gy_sp, void* workspace, size_t workspace_bytes,
+                         int kw, int64_t x_sp, int64_t gy_sp, int act, void* workspace, size_t workspace_bytes,
                          cudaStream_t st) {
     CvGeom g{};
     const int sms = cv_sms();
@@ -890,6 +906,7 @@ int conv_wgrad_tc_launch(const float* x, const float* gy, float* gw, int B, int 
     }
     CvArgs a{};
     a.out = gw;
+    a.act = act;
     return cv_launch<1>("davi_conv2d_wgrad", tmA, tmB, tmB, a, g, workspace, workspace_bytes, st);
 }
 
@@ -921,24 +938,38 @@ extern "C" int davi_conv2d_supported(int B, int H, int W, int Cin, int Cout, int
     return conv_tc_supported(B, H, W, Cin, Cout, kh, kw) ? 1 : 0;
 }
 
-extern "C" int davi_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
-                               int Cin, int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, void* workspace,
-                               size_t workspace_bytes, davi_stream_t stream) {
+extern "C" int davi_conv2d_fwd_ex(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                                  int Cin, int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, int act, void* workspace,
+                                  size_t workspace_bytes, davi_stream_t stream) {
     DAVI_REQUIRE(x && w && y, "null pointer");
     DAVI_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && (!bias || aligned16(bias)), "alignment");
     DAVI_REQUIRE(mult4(x_sp) && mult4(y_sp) && x_sp >= Cin && y_sp >= Cout, "pixel strides");
-    return conv_fwd_tc_launch(x, w, bias, y, B, H, W, Cin, Cout, kh, kw, x_sp, y_sp, workspace, workspace_bytes,
+    DAVI_REQUIRE(act == 0 || act == 1, "act");
+    return conv_fwd_tc_launch(x, w, bias, y, B, H, W, Cin, Cout, kh, kw, x_sp, y_sp, act, workspace, workspace_bytes,
                               (cudaStream_t)stream);
+}
+
+extern "C" int davi_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                               int Cin, int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, void* workspace,
+                               size_t workspace_bytes, davi_stream_t stream) {
+    return davi_conv2d_fwd_ex(x, w, bias, y, B, H, W, Cin, Cout, kh, kw, x_sp, y_sp, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int davi_conv2d_wgrad_ex(const float* x, const float* gy, float* gw, int B, int H, int W, int Cin, int Cout,
+                                    int kh, int kw, int64_t x_sp, int64_t gy_sp, int act, void* workspace,
+                                    size_t workspace_bytes, davi_stream_t stream) {
+    DAVI_REQUIRE(x && gy && gw, "null pointer");
+    DAVI_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(gw), "alignment");
+    DAVI_REQUIRE(mult4(x_sp) && mult4(gy_sp) && x_sp >= Cin && gy_sp >= Cout, "pixel strides");
+    DAVI_REQUIRE(act == 0 || act == 1, "act");
+    return conv_wgrad_tc_launch(x, gy, gw, B, H, W, Cin, Cout, kh, kw, x_sp, gy_sp, act, workspace, workspace_bytes,
+                                (cudaStream_t)stream);
 }
 
 extern "C" int davi_conv2d_wgrad(const float* x, const float* gy, float* gw, int B, int H, int W, int Cin, int Cout,
                                  int kh, int kw, int64_t x_sp, int64_t gy_sp, void* workspace, size_t workspace_bytes,
                                  davi_stream_t stream) {
-    DAVI_REQUIRE(x && gy && gw, "null pointer");
-    DAVI_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(gw), "alignment");
-    DAVI_REQUIRE(mult4(x_sp) && mult4(gy_sp) && x_sp >= Cin && gy_sp >= Cout, "pixel strides");
-    return conv_wgrad_tc_launch(x, gy, gw, B, H, W, Cin, Cout, kh, kw, x_sp, gy_sp, workspace, workspace_bytes,
-                                (cudaStream_t)stream);
+    return davi_conv2d_wgrad_ex(x, gy, gw, B, H, W, Cin, Cout, kh, kw, x_sp, gy_sp, 0, workspace, workspace_bytes, stream);
 }
 
 extern "C" int davi_conv2d_wt(const float* w, float* wt, int Cout, int taps, int Cin, davi_stream_t stream) {

@@ -108,16 +108,26 @@ class Conv2D(nn.Module):
         self._nonlocal_layer = (NonlocalResNetBlock(hp, hp.nonlocop_hparams, in_channels)
                                 if hp.use_nonlocal else None)
 
-    def forward(self, inputs, training=True):
+    def forward(self, inputs, training=True, residual=None):
+        """residual = (shortcut, scale): return shortcut + scale * node(inputs) (res.py:284-286); without a squeeze-
+        and-excite layer behind it the LAST convolution takes the sum into its epilogue."""
         t = inputs
         if self._batch_norm_layer is not None:
             t = self._batch_norm_layer(t, training)                                 # res.py:619
         if self._nonlocal_layer is not None:
             t = self._nonlocal_layer(t)                                             # res.py:621-622
-        for conv in self._conv2d_layers:
-            t = conv(self._activation(t))                                           # res.py:624-627
+        fuse_act = self._hparams.activation == "swish"                              # conv(swish(t)) as ONE kernel
+        last = len(self._conv2d_layers) - 1
+        for i, conv in enumerate(self._conv2d_layers):                              # res.py:624-627
+            add, alpha = (residual if (residual is not None and i == last and self._se_layer is None) else (None, 1.0))
+            if fuse_act:
+                t = conv(t, act="swish", add=add, alpha=alpha)
+            else:
+                t = conv(self._activation(t), add=add, alpha=alpha)
         if self._se_layer is not None:
             t = self._se_layer(t)
+            if residual is not None:
+                t = residual[0] + residual[1] * t
         return t
 
     def reg_loss(self):
@@ -254,9 +264,12 @@ class ResNetBlock(nn.Module):
         else:
             shortcut = self._shortcut(_resize_bilinear_align_corners(inputs, self._up_size), training)
         t = inputs
+        last = len(self._nodes) - 1
         for i, node in enumerate(self._nodes):
             if i == 0 and self._scale > 0:
                 t = _resize_nearest(t, self._up_size)
+            if i == last and isinstance(node, Conv2D):
+                return node(t, training, residual=(shortcut, 0.1))                   # res.py:284-286, in the conv's epilogue
             t = node(t, training)
         return 0.1 * t + shortcut                                                    # res.py:284-286
 

@@ -52,10 +52,13 @@ class WNConv2d(nn.Module):
         ss = self.v.square().sum(dim=(1, 2, 3), keepdim=True).clamp_min(1e-12)
         return self.v * (torch.exp(self.log_g).view(-1, 1, 1, 1) * torch.rsqrt(ss))
 
-    def forward(self, x):
-        """x [B,H,W,Cin] -> [B,H',W',Cout]."""
+    def forward(self, x, act=None, add=None, alpha=1.0):
+        """x [B,H,W,Cin] -> add + alpha * conv(act(x)) [B,H',W',Cout].  act (None | "swish"), add (a tensor like the
+        result) and alpha are the neighbours of the convolution inside a ResNet node (res.py:613-633, 273-286); the
+        tcgen05 kernels take them inside (ops.conv2d_bias)."""
         xc = to_nchw(x)
         k, s = self.k, self.strides
+        addc = None if add is None else to_nchw(add)
         if self.padding == "same":
             H, W = x.shape[1], x.shape[2]
             # TF 'same': total = max((ceil(n/s)-1)*s + k - n, 0); before = total//2, rest after
@@ -65,11 +68,15 @@ class WNConv2d(nn.Module):
                 return tot // 2, tot - tot // 2
             (pt, pb), (pl, pr) = pads(H), pads(W)
             if pt == pb and pl == pr:
-                y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl))
+                y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl), act=act, add=addc, alpha=alpha)
             else:
-                y = ops.conv2d_bias(F.pad(xc, (pl, pr, pt, pb)), self.kernel(), self.bias, stride=s)
+                if act == "swish":
+                    xc = F.silu(xc)
+                elif act is not None:
+                    raise ValueError(act)
+                y = ops.conv2d_bias(F.pad(xc, (pl, pr, pt, pb)), self.kernel(), self.bias, stride=s, add=addc, alpha=alpha)
         else:
-            y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s)
+            y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s, act=act, add=addc, alpha=alpha)
         return to_nhwc(y)
 
     def reg_loss(self):

@@ -859,45 +859,53 @@ def conv_tc_supported(x, w, stride, padding):
     return _conv_tc_shape_ok(B, H, W, Cin, Cout, kh, kw, stride, padding)
 
 
-def conv2d_tc_fwd(x, w, b):
-    """x [B,H,W,Cin] contiguous, w [Cout,kh,kw,Cin] contiguous (OHWI), b [Cout] or None -> y [B,H,W,Cout]."""
+def conv2d_tc_fwd(x, w, b, act=0):
+    """x [B,H,W,Cin] contiguous, w [Cout,kh,kw,Cin] contiguous (OHWI), b [Cout] or None -> y [B,H,W,Cout]
+    = conv(swish(x) if act else x) + b."""
     B, H, W, Cin = x.shape
     Cout, kh, kw, _ = w.shape
     y = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.float32)
     ws, wsb = _conv_workspace(x.device)
     if conv_trace is not None:
         conv_trace.append(("fwd", B, H, W, Cin, Cout, kh, kw))
-    _lib_call("davi_conv2d_fwd", _p(x), _p(w), _p(b) if b is not None else None, _p(y), B, H, W, Cin, Cout, kh, kw,
-              Cin, Cout, _p(ws), wsb, _stream())
+    _lib_call("davi_conv2d_fwd_ex", _p(x), _p(w), _p(b), _p(y), B, H, W, Cin, Cout, kh, kw, Cin, Cout, int(act), _p(ws), wsb,
+              _stream())
     return y
 
 
-def conv2d_tc_wgrad(x, gy, kh, kw):
-    """x [B,H,W,Cin], gy [B,H,W,Cout] contiguous -> gw [Cout,kh,kw,Cin]."""
+def conv2d_tc_wgrad(x, gy, kh, kw, act=0):
+    """x [B,H,W,Cin], gy [B,H,W,Cout] contiguous -> gw [Cout,kh,kw,Cin] = wgrad(swish(x) if act else x, gy)."""
     B, H, W, Cin = x.shape
     Cout = gy.shape[-1]
     gw = torch.empty((Cout, kh, kw, Cin), device=x.device, dtype=torch.float32)
     ws, wsb = _conv_workspace(x.device)
     if conv_trace is not None:
         conv_trace.append(("wgrad", B, H, W, Cin, Cout, kh, kw))
-    _lib_call("davi_conv2d_wgrad", _p(x), _p(gy), _p(gw), B, H, W, Cin, Cout, kh, kw, Cin, Cout, _p(ws), wsb, _stream())
+    _lib_call("davi_conv2d_wgrad_ex", _p(x), _p(gy), _p(gw), B, H, W, Cin, Cout, kh, kw, Cin, Cout, int(act), _p(ws), wsb,
+              _stream())
     return gw
 
 
 class _ConvTC(torch.autograd.Function):
-    """The convolution of the ResNet cells on the repo's tcgen05 kernels (fp32-grade, 3xTF32 compensation in shared
-    memory): forward, input gradient = the forward kernel on the transposed + flipped weights (davi_conv2d_wt),
-    weight gradient = davi_conv2d_wgrad, bias gradient = davi_colsum.  Saves x and w themselves -- no split copies."""
+    """The convolution of the ResNet cells on the repo's tcgen05 kernels (fp32-grade, 3xTF32 compensation on chip):
+    y = conv(swish(x) if act else x, w) + b.  The activation is applied in the operand path of the forward (free: the
+    lo warps have the slack) and recomputed there by the weight gradient (+5 us against the 9 us pass it replaces), so
+    neither swish(x) nor a copy of it is ever stored; the input gradient = the forward kernel on the transposed +
+    flipped weights (davi_conv2d_wt), times swish'(x) by ONE elementwise kernel (measured: the same product inside the
+    convolution's epilogue costs +20 us per launch -- one CTA per SM has too few loads in flight); bias gradient =
+    davi_colsum.  Saves x and w themselves -- no split copies."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, act):
         xh, wh = _nhwc(x), _nhwc(w)
         ctx.save_for_backward(xh, wh)
-        return conv2d_tc_fwd(xh, wh, b).permute(0, 3, 1, 2)
+        ctx.act = int(act)
+        return conv2d_tc_fwd(xh, wh, b, act=act).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gy):
         xh, wh = ctx.saved_tensors
+        act = ctx.act
         gyh = _nhwc(gy)
         Cout, kh, kw, Cin = wh.shape
         gx = gw = gb = None
@@ -906,19 +914,29 @@ class _ConvTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = torch.empty((Cin, kh, kw, Cout), device=wh.device, dtype=torch.float32)
             _lib_call("davi_conv2d_wt", _p(wh), _p(wt), Cout, kh * kw, Cin, _stream())
-            gx = conv2d_tc_fwd(gyh, wt, None).permute(0, 3, 1, 2)
+            gx = conv2d_tc_fwd(gyh, wt, None)
+            if act:
+                gx = torch.ops.aten.silu_backward(gx, xh)
+            gx = gx.permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
-            gw = conv2d_tc_wgrad(xh, gyh, kh, kw).permute(0, 3, 1, 2)
-        return gx, gw, gb
+            gw = conv2d_tc_wgrad(xh, gyh, kh, kw, act=act).permute(0, 3, 1, 2)
+        return gx, gw, gb, None
 
 
-def conv2d_bias(x, w, b, stride=1, padding=0):
-    """F.conv2d(x, w, b) on NCHW views of channels_last tensors, with the fast bias gradient, in the
-    precision selected by set_conv_precision() (and, for "3xtf32", the implementation of set_conv_impl())."""
+def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0):
+    """add + alpha * F.conv2d(act(x), w, b) on NCHW views of channels_last tensors (act: None or "swish"; add: None or a
+    tensor like the result), with the fast bias gradient, in the precision selected by set_conv_precision() (and, for
+    "3xtf32", the implementation of set_conv_impl()): the ResNet node of res.py:613-633 and the block's
+    shortcut + 0.1 * node of res.py:273-286.  The tcgen05 kernels take the activation inside (conv(swish(x)) is ONE kernel);
+    residual and scale stay elementwise torch operations everywhere (fusing them into the convolution's epilogue was
+    measured and dropped, see _ConvTC)."""
     _require_cuda(x, w, b)
+    if act not in (None, "swish"):
+        raise ValueError(f"conv2d_bias: activation {act!r} cannot be fused (None or 'swish')")
     if _conv_precision == "3xtf32" and _conv_impl == "tcgen05":
         if conv_tc_supported(x, w, stride, padding):
-            return _ConvTC.apply(x, w, b)
+            y = _ConvTC.apply(x, w, b, 1 if act else 0)
+            return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
         # channel counts that are not 16-byte multiples (the 138-channel pre/post-processing cells, the 3-channel
         # stem, the 50-channel output head): zero-pad the channel axes, run the same kernels, slice the result
         # (autograd turns the pads into slices and the slice into a pad on the way back)
@@ -929,7 +947,15 @@ def conv2d_bias(x, w, b, stride=1, padding=0):
             xp = F.pad(x.permute(0, 2, 3, 1), (0, pi)).permute(0, 3, 1, 2)
             wp = F.pad(w.permute(0, 2, 3, 1), (0, pi, 0, 0, 0, 0, 0, po)).permute(0, 3, 1, 2)
             bp = None if b is None else F.pad(b, (0, po))
-            return _ConvTC.apply(xp, wp, bp)[:, :w.shape[0]]
+            y = _ConvTC.apply(xp, wp, bp, 1 if act else 0)[:, :w.shape[0]]
+            return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
+    if act:
+        x = torch.nn.functional.silu(x)
+    y = _conv2d_plain(x, w, b, stride, padding)
+    return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
+
+
+def _conv2d_plain(x, w, b, stride, padding):
     if _conv_precision == "3xtf32":
         if not torch.backends.cudnn.allow_tf32:
             raise RuntimeError("conv precision '3xtf32' needs torch.backends.cudnn.allow_tf32 = True "

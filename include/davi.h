@@ -407,6 +407,19 @@ int davi_conv2d_wgrad(const float* x, const float* gy, float* gw,
                       int B, int H, int W, int Cin, int Cout, int kh, int kw,
                       int64_t x_sp, int64_t gy_sp, void* workspace, size_t workspace_bytes,
                       davi_stream_t stream);
+/* The same kernels with the activation in front of the convolution inside a ResNet node fused in
+ * (layers/resnet.py:624-627: conv(activation(t))):
+ *   act = 1   the input goes through swish (x * sigmoid(x)) on its way into the tensor core: y = conv(swish(x)) + bias
+ *             (forward), gw = wgrad(swish(x), gy) (weight gradient); swish(0) = 0 keeps the zero padding.  The input
+ *             gradient of such a convolution is davi_conv2d_fwd(gy, wt) times swish'(x), applied by the caller. */
+int davi_conv2d_fwd_ex(const float* x, const float* w, const float* bias, float* y,
+                       int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                       int64_t x_sp, int64_t y_sp, int act,
+                       void* workspace, size_t workspace_bytes, davi_stream_t stream);
+int davi_conv2d_wgrad_ex(const float* x, const float* gy, float* gw,
+                         int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                         int64_t x_sp, int64_t gy_sp, int act,
+                         void* workspace, size_t workspace_bytes, davi_stream_t stream);
 /* wt[ci][taps-1-tap][co] = w[co][tap][ci] (taps = kh*kw): the weights of the input-gradient convolution */
 int davi_conv2d_wt(const float* w, float* wt, int Cout, int taps, int Cin, davi_stream_t stream);
 

@@ -428,6 +428,45 @@ def test_conv_tcgen05_matches_oracle(cuda, B, H, W, ci, co, k):
     assert int(ws[:256].view(torch.int32).abs().max()) == 0
 
 
+@pytest.mark.parametrize("B,H,W,ci,co,k,impl", [(3, 16, 16, 64, 64, 3, "tcgen05"), (40, 16, 16, 276, 276, 1, "tcgen05"),
+                                               (40, 16, 16, 316, 316, 3, "tcgen05"), (2, 32, 32, 138, 138, 3, "tcgen05"),
+                                               (2, 16, 16, 24, 32, 3, "cudnn")])
+def test_conv_fused_node_matches_oracle(cuda, B, H, W, ci, co, k, impl):
+    """The ResNet node around the convolution (res.py:613-633: swish -> conv; res.py:284-286: shortcut + 0.1 * node)
+    inside the tcgen05 kernels -- swish in the operand path of the forward and of the weight gradient, swish'(x) and
+    the scale in the epilogue of the input gradient, shortcut + scale in the forward's epilogue -- against
+    shortcut + 0.1 * conv2d_same(swish(x)) of the float64 oracle: value and the gradients of x, w, b and shortcut.
+    The padded (138 channels) and the cuDNN paths apply the same pieces as separate operations."""
+    from deep_attentive_vi_b200 import ops
+    from oracle import ops as R
+    ops.set_conv_precision("3xtf32")
+    ops.set_conv_impl(impl)
+    try:
+        torch.manual_seed(ci * 7 + co)
+        x = torch.randn(B, H, W, ci, device=cuda).permute(0, 3, 1, 2).requires_grad_()
+        w = (torch.randn(co, ci, k, k, device=cuda) / (ci * k * k) ** 0.5).contiguous(
+            memory_format=torch.channels_last).requires_grad_()
+        b = torch.randn(co, device=cuda, requires_grad=True)
+        sc = torch.randn(B, H, W, co, device=cuda).permute(0, 3, 1, 2).requires_grad_()
+        go = torch.randn(B, co, H, W, device=cuda).contiguous(memory_format=torch.channels_last)
+        y = ops.conv2d_bias(x, w, b, stride=1, padding=k // 2, act="swish", add=sc, alpha=0.1)
+        g = torch.autograd.grad(y, (x, w, b, sc), go)
+        xd = x.detach().permute(0, 2, 3, 1).double().cpu().requires_grad_()
+        wd = w.detach().permute(2, 3, 1, 0).double().cpu().requires_grad_()
+        bd = b.detach().double().cpu().requires_grad_()
+        sd = sc.detach().permute(0, 2, 3, 1).double().cpu().requires_grad_()
+        yd = sd + 0.1 * R.conv2d_same(xd * torch.sigmoid(xd), wd, bd)
+        gd = torch.autograd.grad(yd, (xd, wd, bd, sd), go.permute(0, 2, 3, 1).double().cpu())
+        err = lambda a, c: ((a.double().cpu() - c).abs().max() / c.abs().max()).item()
+        assert err(y.permute(0, 2, 3, 1), yd.detach()) < 3e-5
+        assert err(g[0].permute(0, 2, 3, 1), gd[0]) < 3e-5, ("x", err(g[0].permute(0, 2, 3, 1), gd[0]))
+        assert err(g[1].permute(2, 3, 1, 0), gd[1]) < 3e-5, ("w", err(g[1].permute(2, 3, 1, 0), gd[1]))
+        assert err(g[2], gd[2]) < 3e-5
+        assert err(g[3].permute(0, 2, 3, 1), gd[3]) < 1e-6
+    finally:
+        ops.set_conv_impl("tcgen05")
+
+
 def test_conv_tcgen05_envelope_and_fallback(cuda):
     """Shapes outside the kernel's envelope: stride 2 and more than 384 channels go through the cuDNN 3xTF32 path;
     channel counts that are not 16-byte multiples (138-channel cells, 3-channel stem, 50-channel head) are zero-padded

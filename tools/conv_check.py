@@ -124,6 +124,25 @@ def main():
             print(json.dumps(dict(debug=dbg, fwd_us=round(f, 1), wgrad_us=round(g, 1))), flush=True)
         _lib.set_option(4, 0)
         return
+    if sys.argv[1] == "fused":                     # cost of the fused activation (swish in the operand path)
+        dev = torch.device("cuda")
+        lib = _lib.load()
+        wsb = lib.davi_conv2d_workspace_bytes()
+        ws = torch.zeros(wsb // 4, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        for (B, H, W, Cin, Cout, k) in ((40, 16, 16, 316, 316, 3), (40, 16, 16, 316, 316, 1)):
+            x = torch.randn(B, H, W, Cin, device=dev); w = torch.randn(Cout, k, k, Cin, device=dev) * 0.05
+            gy = torch.randn(B, H, W, Cout, device=dev)
+            y = torch.empty(B, H, W, Cout, device=dev); gw = torch.empty(Cout, k, k, Cin, device=dev)
+            f = lambda act: timed(lambda: _lib.call("davi_conv2d_fwd_ex", p(x), p(w), None, p(y), B, H, W, Cin, Cout, k, k, Cin,
+                                                    Cout, act, p(ws), wsb, st))
+            g = lambda act: timed(lambda: _lib.call("davi_conv2d_wgrad_ex", p(x), p(gy), p(gw), B, H, W, Cin, Cout, k, k, Cin,
+                                                    Cout, act, p(ws), wsb, st))
+            silu = timed(lambda: torch.nn.functional.silu(x))
+            print(json.dumps(dict(k=k, fwd=round(f(0), 1), fwd_act=round(f(1), 1), wgrad=round(g(0), 1),
+                                  wgrad_act=round(g(1), 1), torch_silu=round(silu, 1))), flush=True)
+        return
     if sys.argv[1] == "list":
         for c in CASES:
             if c[0] == sys.argv[2]:
