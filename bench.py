@@ -500,6 +500,8 @@ def run_davi(args):
     from deep_attentive_vi_b200.util.trainer import Trainer
 
     world, rank, local, device = dist_setup()
+    if args.conv_sm_reserve >= 0:
+        _lib.set_option(_lib.OPT_CONV_SM_RESERVE, args.conv_sm_reserve)
     wl = TRAIN_WORKLOADS[args.workload]
     flags = getattr(M, wl["flags"])
     B = args.batch or wl["batch"]
@@ -877,6 +879,9 @@ def main():
     ap.add_argument("--fp32-convs", action="store_true", help="same as --convs fp32")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--conv-sm-reserve", type=int, default=-1,
+                    help="SMs the convolution grids leave free for the NCCL kernels of the overlapped gradient exchange "
+                         "(-1 = the trainer's default: 0 on one GPU)")
     ap.add_argument("--roofline-detail", default="", help="write the per-launch dw-attention timings here")
     ap.add_argument("--dw-trace-out", default="", help="write the recorded dw-attention launch structure here")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -67,7 +67,7 @@ SIGNATURES = {
 
 
 # davi_set_option switches (include/davi.h)
-OPT_DW_IMPL, OPT_NONLOCAL_IMPL, OPT_NL_DS, OPT_NL_BWD = 0, 1, 2, 3
+OPT_DW_IMPL, OPT_NONLOCAL_IMPL, OPT_NL_DS, OPT_NL_BWD, OPT_CONV_DEBUG, OPT_CONV_SM_RESERVE = 0, 1, 2, 3, 4, 5
 
 
 class DaviError(RuntimeError):

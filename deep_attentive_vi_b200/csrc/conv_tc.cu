@@ -736,7 +736,12 @@ __global__ void __launch_bounds__(128) conv_reduce_kernel(const CvArgs a, const 
 // ---- host side ----------------------------------------------------------------------------------------
 
 static int cv_pairs_for(int tiles, int kch, int sms) {
-    int pmax = sms / 2;
+    // DAVI_OPT_CONV_SM_RESERVE: SMs left free for kernels that run beside the convolutions (the NCCL kernels of the
+    // overlapped gradient exchange): a CTA pair that finds no free TPC starts only when another pair has finished
+    int reserve = get_option(DAVI_OPT_CONV_SM_RESERVE);
+    if (reserve < 0) reserve = 0;
+    if (reserve > sms - 8) reserve = sms - 8;
+    int pmax = (sms - reserve) / 2;
     if (pmax > kCvMaxPairs) pmax = kCvMaxPairs;
     if (pmax < 1) pmax = 1;
     const int64_t units = (int64_t)tiles * kch;

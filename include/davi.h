@@ -58,6 +58,7 @@ int davi_last_error(char* buf, size_t buf_bytes);
 #define DAVI_OPT_NL_DS 2          /* 1: per-block dQ/dK variant also for N = 256                */
 #define DAVI_OPT_NL_BWD 3         /* 1: nonlocal gradient as three launches instead of one      */
 #define DAVI_OPT_CONV_DEBUG 4      /* profiling only (WRONG results): bits: 1 no lo arithmetic, 2 one MMA of three, 4 no stores, 8 256+rest column split, 16 / 32 no A / B loads */
+#define DAVI_OPT_CONV_SM_RESERVE 5 /* SMs the convolution grids leave free (for concurrently running NCCL kernels)        */
 #define DAVI_OPT_COUNT_ 8
 int davi_set_option(int option, int value);
 int davi_get_option(int option);

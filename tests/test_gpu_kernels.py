@@ -467,6 +467,43 @@ def test_conv_fused_node_matches_oracle(cuda, B, H, W, ci, co, k, impl):
         ops.set_conv_impl("tcgen05")
 
 
+def test_conv_tcgen05_strided_views_through_the_abi(cuda, libdavi):
+    """The C ABI takes pixel strides: input, output and output gradient may be channel slices of wider tensors
+    (x_sp > Cin, y_sp > Cout) -- davi_conv2d_fwd_ex (with and without the fused swish) and davi_conv2d_wgrad_ex
+    called directly on such views against the oracle."""
+    import ctypes
+    from deep_attentive_vi_b200 import _lib
+    from oracle import ops as R
+    torch.manual_seed(5)
+    B, H, W, ci, co, k = 3, 16, 16, 40, 72, 3
+    xw = torch.randn(B, H, W, ci + 24, device=cuda)               # x = channels 8 .. 8 + ci of a wider tensor
+    yw = torch.full((B, H, W, co + 12), 7.0, device=cuda)         # y = channels 4 .. 4 + co
+    gyw = torch.randn(B, H, W, co + 8, device=cuda)
+    w = (torch.randn(co, k, k, ci, device=cuda) / (ci * k * k) ** 0.5)
+    b = torch.randn(co, device=cuda)
+    gw = torch.empty(co, k, k, ci, device=cuda)
+    wsb = libdavi.davi_conv2d_workspace_bytes()
+    ws = torch.zeros(wsb // 4, device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    x, y, gy = xw[..., 8:8 + ci], yw[..., 4:4 + co], gyw[..., 4:4 + co]
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    err = lambda a, c: ((a.double().cpu() - c).abs().max() / c.abs().max()).item()
+    for act in (0, 1):
+        _lib.call("davi_conv2d_fwd_ex", p(x), p(w), p(b), p(y), B, H, W, ci, co, k, k, xw.shape[-1], yw.shape[-1], act, p(ws),
+                  wsb, st)
+        _lib.call("davi_conv2d_wgrad_ex", p(x), p(gy), p(gw), B, H, W, ci, co, k, k, xw.shape[-1], gyw.shape[-1], act, p(ws),
+                  wsb, st)
+        xd = x.double().cpu()
+        xin = (xd * torch.sigmoid(xd) if act else xd).requires_grad_()
+        wd = w.permute(1, 2, 3, 0).double().cpu().requires_grad_()
+        yd = R.conv2d_same(xin, wd, b.double().cpu())
+        gwd, = torch.autograd.grad(yd, wd, gy.double().cpu())
+        assert err(y, yd.detach()) < 3e-5
+        assert err(gw.permute(1, 2, 3, 0), gwd) < 3e-5
+        assert bool((yw[..., :4] == 7.0).all()) and bool((yw[..., 4 + co:] == 7.0).all())      # neighbours untouched
+    assert int(ws[:256].view(torch.int32).abs().max()) == 0
+
+
 def test_conv_tcgen05_envelope_and_fallback(cuda):
     """Shapes outside the kernel's envelope: stride 2 and more than 384 channels go through the cuDNN 3xTF32 path;
     channel counts that are not 16-byte multiples (138-channel cells, 3-channel stem, 50-channel head) are zero-padded
