@@ -933,12 +933,7 @@ def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0):
     _require_cuda(x, w, b)
     if act not in (None, "swish"):
         raise ValueError(f"conv2d_bias: activation {act!r} cannot be fused (None or 'swish')")
-    # Forward-only passes over large batches (the importance-sampled evaluation: 16 images x 25 samples per call) hold
-    # several full tiles per CTA pair; with ONE accumulator in TMEM the epilogue of a tile does not overlap the next
-    # tile's MMAs and cuDNN's 3xTF32 path is ~12 % faster end to end (1 998 vs 1 752 sample-images/s, profiles/): the
-    # own kernels are used where they win -- training shapes, any pass that needs gradients
-    big_eval = (not torch.is_grad_enabled()) and x.shape[0] * x.shape[2] * x.shape[3] > 2 * 74 * 256
-    if _conv_precision == "3xtf32" and _conv_impl == "tcgen05" and not big_eval:
+    if _conv_precision == "3xtf32" and _conv_impl == "tcgen05":
         if conv_tc_supported(x, w, stride, padding):
             y = _ConvTC.apply(x, w, b, 1 if act else 0)
             return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
