@@ -55,6 +55,7 @@ SIGNATURES = {
     "davi_split_tf32_dual": (_i, [_f, _f, _f, _l, _i, _i, _i, _s]),
     "davi_conv2d_workspace_bytes": (_z, []),
     "davi_fill_zero": (_i, [_f, _l, _s]),
+    "davi_conv2d_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _lp]),
     "davi_conv2d_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "davi_conv2d_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _f, _z, _s]),
     "davi_conv2d_fwd_ex": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _i, _f, _z, _s]),

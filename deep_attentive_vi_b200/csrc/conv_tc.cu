@@ -833,28 +833,37 @@ static int cv_launch(const char* fn, const CUtensorMap& tmA, const CUtensorMap& 
     return check_launch(fn);
 }
 
+// geometry of a forward / input-gradient launch (mode 0) or a weight-gradient launch (mode 1) on `sms` SMs
+static bool cv_geom(CvGeom& g, int mode, int B, int H, int W, int Cin, int Cout, int kh, int kw, int sms) {
+    if (!cv_common(g, B, H, W, Cin, Cout, kh, kw) || sms < 2) return false;
+    g.mode = mode;
+    if (mode == 0) {
+        g.tiles = B * g.tiles_per_image;
+        g.kch = g.taps * g.cch;
+        // the TMEM-operand pair MMA takes N in multiples of 32
+        g.n_total = (Cout + 31) / 32 * 32;
+        if (g.n_total <= 256) { g.np0 = g.n_total; g.np1 = 0; }
+        else if (get_option(DAVI_OPT_CONV_DEBUG) & 8) { g.np0 = (g.n_total / 2 + 31) / 32 * 32; g.np1 = g.n_total - g.np0; }
+        else { g.np0 = 256; g.np1 = g.n_total - 256; }     // one full-width MMA + the rest: measured 3 % faster than two halves
+    } else {
+        g.tiles = (g.mblocks + 7) / 8;
+        g.kch = B * g.chunks_per_image;
+        g.n_total = (Cout + 63) / 64 * 64;                 // MN-major B: whole 32-column blocks per CTA
+        g.np0 = g.n_total < 256 ? g.n_total : 256;
+        g.np1 = g.n_total - g.np0;
+    }
+    return cv_finish(g, sms);
+}
+
 int conv_fwd_tc_launch(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                        int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, int act, void* workspace,
                        size_t workspace_bytes, cudaStream_t st) {
     CvGeom g{};
-    const int sms = cv_sms();
-    if (!cv_common(g, B, H, W, Cin, Cout, kh, kw) || sms < 2) {
+    if (!cv_geom(g, 0, B, H, W, Cin, Cout, kh, kw, cv_sms())) {
         set_error("davi_conv2d_fwd: shape not supported by the tensor-core kernel");
         return DAVI_EINVAL;
     }
-    g.mode = 0;
-    g.tiles = B * g.tiles_per_image;
-    g.kch = g.taps * g.cch;
-    // the TMEM-operand pair MMA takes N in multiples of 32
-    g.n_total = (Cout + 31) / 32 * 32;
-    if (g.n_total <= 256) { g.np0 = g.n_total; g.np1 = 0; }
-    else if (get_option(DAVI_OPT_CONV_DEBUG) & 8) { g.np0 = (g.n_total / 2 + 31) / 32 * 32; g.np1 = g.n_total - g.np0; }
-    else { g.np0 = 256; g.np1 = g.n_total - 256; }     // one full-width MMA + the rest: measured 3 % faster than two halves
     g.out_sp = y_sp;
-    if (!cv_finish(g, sms)) {
-        set_error("davi_conv2d_fwd: tile does not fit shared memory");
-        return DAVI_EINVAL;
-    }
     CUtensorMap tmA, tmB, tmB1;
     int rc;
     {
@@ -881,19 +890,8 @@ int conv_wgrad_tc_launch(const float* x, const float* gy, float* gw, int B, int 
                          int kw, int64_t x_sp, int64_t gy_sp, int act, void* workspace, size_t workspace_bytes,
                          cudaStream_t st) {
     CvGeom g{};
-    const int sms = cv_sms();
-    if (!cv_common(g, B, H, W, Cin, Cout, kh, kw) || sms < 2) {
+    if (!cv_geom(g, 1, B, H, W, Cin, Cout, kh, kw, cv_sms())) {
         set_error("davi_conv2d_wgrad: shape not supported by the tensor-core kernel");
-        return DAVI_EINVAL;
-    }
-    g.mode = 1;
-    g.tiles = (g.mblocks + 7) / 8;
-    g.kch = B * g.chunks_per_image;
-    g.n_total = (Cout + 63) / 64 * 64;
-    g.np0 = g.n_total < 256 ? g.n_total : 256;
-    g.np1 = g.n_total - g.np0;
-    if (!cv_finish(g, sms)) {
-        set_error("davi_conv2d_wgrad: tile does not fit shared memory");
         return DAVI_EINVAL;
     }
     CUtensorMap tmA, tmB;
@@ -913,6 +911,20 @@ int conv_wgrad_tc_launch(const float* x, const float* gy, float* gw, int B, int 
     a.out = gw;
     a.act = act;
     return cv_launch<1>("davi_conv2d_wgrad", tmA, tmB, tmB, a, g, workspace, workspace_bytes, st);
+}
+
+// plan[0..11] = tiles, k-chunks per tile, CTA pairs, accumulator columns, columns of MMA 0, of MMA 1, hi-ring stages,
+// lo-ring slots, reduce mode, dynamic shared memory bytes, workspace bytes needed, staged-tile epilogue available
+int conv_plan(int mode, int B, int H, int W, int Cin, int Cout, int kh, int kw, int sms, int64_t* plan) {
+    CvGeom g{};
+    if (!cv_geom(g, mode, B, H, W, Cin, Cout, kh, kw, sms)) return DAVI_EINVAL;
+    const int64_t n_pad = (g.n_total + 31) / 32 * 32;
+    plan[0] = g.tiles; plan[1] = g.kch; plan[2] = g.pairs; plan[3] = g.n_total; plan[4] = g.np0; plan[5] = g.np1;
+    plan[6] = g.stages; plan[7] = g.slots; plan[8] = g.reduce;
+    plan[9] = 1024 + (int64_t)g.stages * (kCvABytes + g.nb * 128) + (int64_t)g.slots * g.nb * 128 + kCvStageBytes;
+    plan[10] = kCvFlagBytes + (int64_t)g.pairs * (g.reduce ? 2 : 1) * 2 * 128 * n_pad * 4;
+    plan[11] = g.tile_ok;
+    return DAVI_OK;
 }
 
 int conv_wt_launch(const float* w, float* wt, int Cout, int taps, int Cin, cudaStream_t st) {
@@ -937,6 +949,13 @@ extern "C" int davi_fill_zero(float* dst, int64_t n, davi_stream_t stream) {
     DAVI_REQUIRE(dst && n >= 0, "null pointer / negative size");
     DAVI_CUDA(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(float), (cudaStream_t)stream));
     return DAVI_OK;
+}
+
+extern "C" int davi_conv2d_plan(int mode, int B, int H, int W, int Cin, int Cout, int kh, int kw, int sms, int64_t* plan) {
+    DAVI_REQUIRE(plan && (mode == 0 || mode == 1) && sms >= 2, "arguments");
+    const int rc = conv_plan(mode, B, H, W, Cin, Cout, kh, kw, sms, plan);
+    if (rc) set_error("davi_conv2d_plan: shape outside the envelope of the tensor-core kernels");
+    return rc;
 }
 
 extern "C" int davi_conv2d_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw) {

@@ -400,6 +400,11 @@ size_t davi_conv2d_workspace_bytes(void);
 /* dst[0 : n] = 0 on `stream` (the one-time zero fill of the workspace for callers without a memset of their own) */
 int davi_fill_zero(float* dst, int64_t n, davi_stream_t stream);
 int davi_conv2d_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw);
+/* Host-only: how a launch on a GPU with `sms` SMs would be laid out (no device needed; for tests and capacity planning).
+ * mode 0 = forward / input gradient, 1 = weight gradient.  plan[0..11] = tiles, k-chunks per tile, CTA pairs, accumulator
+ * columns, columns of MMA 0, of MMA 1, TMA ring stages, lo-ring slots, reduce mode (0/1), dynamic shared memory bytes,
+ * workspace bytes needed, staged-tile epilogue available (0/1). */
+int davi_conv2d_plan(int mode, int B, int H, int W, int Cin, int Cout, int kh, int kw, int sms, int64_t* plan);
 int davi_conv2d_fwd(const float* x, const float* w, const float* bias, float* y,
                     int B, int H, int W, int Cin, int Cout, int kh, int kw,
                     int64_t x_sp, int64_t y_sp, void* workspace, size_t workspace_bytes,

@@ -251,3 +251,32 @@ def test_bucketed_all_reduce_with_gloo():
         mp.spawn(_bucket_worker, args=(world, port, ret), nprocs=world, join=True)
         assert ret["err"] == 0.0
         assert ret["nb"] >= 3 and ret["order"] == sorted(ret["order"], reverse=True)   # last layers' buckets first
+
+
+def test_convolution_launch_plans_of_the_model_shapes(libdavi):
+    """davi_conv2d_plan (host-only): every convolution shape of the CIFAR-10 / OMNIGLOT models, forward, input gradient
+    and weight gradient on 148 SMs, fits shared memory (227 KB) and TMEM (512 columns), keeps at least two ring stages,
+    stays inside the workspace bound, and cuts its (tile, k-chunk) units so that no CTA pair idles."""
+    import ctypes
+    shapes = [(40, 16, 16, 276, 276, 3), (40, 16, 16, 316, 316, 3), (40, 16, 16, 296, 296, 3), (40, 16, 16, 276, 40, 3),
+              (40, 16, 16, 276, 340, 1), (40, 16, 16, 316, 380, 1), (40, 16, 16, 296, 360, 1), (40, 16, 16, 276, 256, 1),
+              (40, 32, 32, 140, 140, 3), (40, 32, 32, 4, 140, 3), (40, 32, 32, 140, 52, 3), (40, 32, 32, 140, 204, 1),
+              (16, 16, 16, 72, 72, 3), (16, 16, 16, 88, 88, 3), (16, 32, 32, 36, 36, 3), (400, 16, 16, 316, 316, 3),
+              (1, 16, 16, 8, 8, 1), (2, 32, 8, 36, 40, 3)]
+    wsb = libdavi.davi_conv2d_workspace_bytes()
+    for (B, H, W, ci, co, k) in shapes:
+        for mode, cin, cout in ((0, ci, co), (0, co, ci), (1, ci, co)):        # forward, input gradient, weight gradient
+            plan = (ctypes.c_int64 * 12)()
+            assert libdavi.davi_conv2d_supported(B, H, W, cin, cout, k, k) == 1
+            assert libdavi.davi_conv2d_plan(mode, B, H, W, cin, cout, k, k, 148, plan) == 0, (mode, B, H, W, cin, cout, k)
+            tiles, kch, pairs, n_total, np0, np1, stages, slots, reduce, smem, ws, tile_ok = list(plan)
+            assert 1 <= pairs <= 74 and pairs <= tiles * kch
+            assert n_total == np0 + np1 and np0 % 32 == 0 and np1 % 32 == 0 and np0 <= 256 and n_total >= cout
+            assert n_total + 64 * slots <= 512 and slots >= 2 and stages >= 2
+            assert smem <= 227 * 1024 and ws <= wsb
+            if reduce:
+                assert -(-tiles * kch // pairs) <= kch             # at most two segments per pair
+    plan = (ctypes.c_int64 * 12)()
+    assert libdavi.davi_conv2d_supported(40, 16, 16, 276, 584, 1, 1) == 0       # more than 384 channels
+    assert libdavi.davi_conv2d_plan(0, 40, 16, 16, 276, 584, 1, 1, 148, plan) != 0
+    assert libdavi.davi_conv2d_supported(40, 32, 32, 138, 138, 3, 3) == 0       # rows that are not 16-byte multiples
