@@ -19,9 +19,12 @@ gathered) is recorded and replayed stand-alone on cold operands (`frac`), and
 the same launches are timed inside an eager step (`in_step`); `traffic` is read
 from the committed ncu capture of those launches (profiles/).
 `roofline_nonlocal` is the tensor-bound view of the nonlocal attention calls,
-`roofline_elbo` the HBM view of the ELBO reductions.  Precision: the hot-path
-kernels compute in fp32 (3xTF32 on the tensor cores); the host-side cuDNN
-convolutions run in 3xTF32 by default (`--convs`, reported as `conv_dtype`).
+`roofline_conv` the same view of the convolution launches of one step (the
+repo's tcgen05 kernels, recorded and replayed per shape), `roofline_elbo` the
+HBM view of the ELBO reductions.  Precision: every kernel computes at fp32
+grade (3xTF32 on the tensor cores); `--convs` selects other convolution paths
+(`3xtf32-cudnn` = the round-1 path: cuDNN over split operands; `fp32`; `tf32`,
+below the reference's precision), reported as `conv_dtype`.
 """
 import argparse
 import json

@@ -6,8 +6,10 @@
 // Precision: the reference convolves in fp32 (TF 2.3 has no TF32), so every product is error-compensated
 // exactly like the nonlocal kernels (nonlocal_tc.cu): v = hi + lo, hi = the fp32 bit pattern (the tensor
 // core truncates it to tf32), lo = rna_tf32(v - trunc(v)); hi*hi' + lo*hi' + hi*lo' accumulated in fp32 in
-// TMEM.  The lo images are computed in SHARED memory from the tiles TMA delivered -- no split tensors in
-// HBM (the cuDNN path needed davi_split_tf32: 24 B written per element) and no tripled contraction axis.
+// TMEM.  The lo images are computed ON CHIP from the tiles TMA delivered -- the A tile goes to TMEM as hi | lo
+// (tcgen05.st; the MMAs read A from TMEM, which took 100 KB per chunk of operand reads off shared memory), the lo
+// image of B is a shared -> shared pass -- no split tensors in HBM (the cuDNN path needed davi_split_tf32: 24 B
+// written per element) and no tripled contraction axis.
 //
 // GEMM view.  MODE 0 (forward / input gradient):
 //     D[m = pixel, n = c_out] = sum_{tap, c_in} X[pixel + tap offset, c_in] * Wt[c_out, tap, c_in]
@@ -16,11 +18,12 @@
 //   B = weights [c_out][tap][c_in] (OHWI, the layout the trainer keeps them in), K-major.
 // MODE 1 (weight gradient):
 //     D[m = (tap, c_in), n = c_out] = sum_{pixel} X[pixel + tap offset, c_in] * GY[pixel, c_out]
-//   both operands MN-major (channels contiguous, pixels strided): TMA boxes [32 ch x 32 pixels] written
-//   with the 32-byte-atom swizzle, the only MN-major layout 32-bit operands have (tc_common.cuh).
+//   both operands have the channels contiguous and the pixels strided: B = gy as MN-major TMA boxes [32 ch x 32 pixels]
+//   (32-byte-atom swizzle, the only MN-major layout 32-bit operands have, tc_common.cuh); A = plain boxes of x that
+//   the lo warps transpose on their way into TMEM (thread = channel reads its 32 pixels).
 //
 // Work decomposition.  A CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256) owns 256 rows of D
-// and ALL of its columns (N <= 512 fp32 columns of TMEM): each CTA stages its own 128 rows of A and HALF
+// and ALL of its columns (N <= 384 fp32 columns of TMEM; the rest holds the A ring): each CTA stages its own 128 rows of A and HALF
 // of B, so B is fetched from L2 once per pair (the single-CTA form would need ~30 B/clk/SM of L2
 // bandwidth for the 3xTF32 operand stream, 70 % of the measured L2 limit).  A 16x16 model at batch 40
 // has only 40 such tiles for 74 pairs, so the K loop is cut stream-K style: the (tile, k-chunk) units
