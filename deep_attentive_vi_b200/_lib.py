@@ -62,6 +62,7 @@ SIGNATURES = {
     "davi_conv2d_wgrad_ex": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _i, _f, _z, _s]),
     "davi_conv2d_wgrad": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _f, _z, _s]),
     "davi_conv2d_wt": (_i, [_f, _f, _i, _i, _i, _s]),
+    "davi_conv2d_wt_batched": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _l, _s]),
     "davi_adamax_step": (_i, [_f, _f, _f, _f, _l, _r, _r, _r, _r, _l, _r, _r, _s]),
     "davi_adamax_step_dev": (_i, [_f, _f, _f, _f, _l, _f, _r, _r, _r, _r, _s]),
 }

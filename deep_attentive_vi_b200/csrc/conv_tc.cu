@@ -686,6 +686,39 @@ __global__ void conv_wt_kernel(const float* __restrict__ w, float* __restrict__ 
     }
 }
 
+// The same for every convolution of a model in ONE launch (the trainer calls it once per step, right after the
+// weight norm): kernels live at offs[i] in a flat array, their transposes at the same offsets of a second one;
+// tile_prefix[i] = number of 32 x 32 tiles of the kernels before i (tile_prefix[count] = grid size).
+__global__ void conv_wt_batched_kernel(const float* __restrict__ w_flat, float* __restrict__ wt_flat,
+                                       const int64_t* __restrict__ offs, const int* __restrict__ couts,
+                                       const int* __restrict__ taps_, const int* __restrict__ cins,
+                                       const int64_t* __restrict__ tile_prefix, int count) {
+    __shared__ float tile[32][33];
+    const int64_t b = blockIdx.x;
+    int lo = 0, hi = count - 1;
+    while (lo < hi) {                                      // last i with tile_prefix[i] <= b
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_prefix[mid] <= b) lo = mid; else hi = mid - 1;
+    }
+    const int Cout = couts[lo], taps = taps_[lo], Cin = cins[lo];
+    const int tci = (Cin + 31) / 32, tco = (Cout + 31) / 32;
+    int64_t local = b - tile_prefix[lo];
+    const int tap = (int)(local / (tci * tco));
+    local -= (int64_t)tap * tci * tco;
+    const int co0 = (int)(local / tci) * 32, ci0 = (int)(local % tci) * 32;
+    const float* w = w_flat + offs[lo];
+    float* wt = wt_flat + offs[lo];
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int co = co0 + i, ci = ci0 + threadIdx.x;
+        tile[i][threadIdx.x] = (co < Cout && ci < Cin) ? w[((int64_t)co * taps + tap) * Cin + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int ci = ci0 + i, co = co0 + threadIdx.x;
+        if (ci < Cin && co < Cout) wt[((int64_t)ci * taps + (taps - 1 - tap)) * Cout + co] = tile[threadIdx.x][i];
+    }
+}
+
 // Weight gradients with few tiles and a long pixel axis (1x1 kernels: 2 tiles x 320 chunks) are cut into dozens of
 // segments per tile; one owner adding them serially would take longer than the MMAs.  In `reduce` mode every
 // segment lands in the workspace and this kernel sums the segments of a tile in pair order (deterministic).
@@ -947,6 +980,16 @@ extern "C" int davi_cv_trace_read(unsigned long long* out) {
 #endif
 
 extern "C" size_t davi_conv2d_workspace_bytes(void) { return conv_tc_workspace_bytes(); }
+
+extern "C" int davi_conv2d_wt_batched(const float* w_flat, float* wt_flat, const int64_t* offs, const int* couts,
+                                      const int* taps, const int* cins, const int64_t* tile_prefix, int count,
+                                      int64_t total_tiles, davi_stream_t stream) {
+    DAVI_REQUIRE(w_flat && wt_flat && w_flat != wt_flat && offs && couts && taps && cins && tile_prefix, "null / aliased pointer");
+    DAVI_REQUIRE(count > 0 && total_tiles > 0 && total_tiles < (int64_t)1 << 31, "table size");
+    conv_wt_batched_kernel<<<(unsigned)total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(w_flat, wt_flat, offs, couts, taps,
+                                                                                          cins, tile_prefix, count);
+    return check_launch("davi_conv2d_wt_batched");
+}
 
 extern "C" int davi_fill_zero(float* dst, int64_t n, davi_stream_t stream) {
     DAVI_REQUIRE(dst && n >= 0, "null pointer / negative size");

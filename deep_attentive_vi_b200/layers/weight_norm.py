@@ -42,6 +42,7 @@ class WNConv2d(nn.Module):
         # set by util/trainer.py: a leaf view into the flat effective-weight array that ONE fused
         # kernel (davi_weight_norm_fwd) fills for all convolutions of the model before the forward
         self._w_override = None
+        self._wt_override = None    # likewise: [Cin,kh,kw,Cout] transposed + flipped image of the kernel (input gradient)
 
     def kernel(self):
         if not self.use_weight_norm:
@@ -59,6 +60,7 @@ class WNConv2d(nn.Module):
         xc = to_nchw(x)
         k, s = self.k, self.strides
         addc = None if add is None else to_nchw(add)
+        wt = self._wt_override if (self.use_weight_norm and self._w_override is not None) else None
         if self.padding == "same":
             H, W = x.shape[1], x.shape[2]
             # TF 'same': total = max((ceil(n/s)-1)*s + k - n, 0); before = total//2, rest after
@@ -68,7 +70,8 @@ class WNConv2d(nn.Module):
                 return tot // 2, tot - tot // 2
             (pt, pb), (pl, pr) = pads(H), pads(W)
             if pt == pb and pl == pr:
-                y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl), act=act, add=addc, alpha=alpha)
+                y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl), act=act, add=addc, alpha=alpha,
+                                    wt=wt)
             else:
                 if act == "swish":
                     xc = F.silu(xc)

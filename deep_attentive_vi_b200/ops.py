@@ -896,10 +896,11 @@ class _ConvTC(torch.autograd.Function):
     davi_colsum.  Saves x and w themselves -- no split copies."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act):
+    def forward(ctx, x, w, b, act, wt):
         xh, wh = _nhwc(x), _nhwc(w)
         ctx.save_for_backward(xh, wh)
         ctx.act = int(act)
+        ctx.wt = wt         # [Cin,kh,kw,Cout]: the trainer's per-step davi_conv2d_wt_batched image of w, or None
         return conv2d_tc_fwd(xh, wh, b, act=act).permute(0, 3, 1, 2)
 
     @staticmethod
@@ -912,22 +913,25 @@ class _ConvTC(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             gb = colsum_nhwc(gy)                                   # first: gy is still L2-resident
         if ctx.needs_input_grad[0]:
-            wt = torch.empty((Cin, kh, kw, Cout), device=wh.device, dtype=torch.float32)
-            _lib_call("davi_conv2d_wt", _p(wh), _p(wt), Cout, kh * kw, Cin, _stream())
+            wt = ctx.wt
+            if wt is None:
+                wt = torch.empty((Cin, kh, kw, Cout), device=wh.device, dtype=torch.float32)
+                _lib_call("davi_conv2d_wt", _p(wh), _p(wt), Cout, kh * kw, Cin, _stream())
             gx = conv2d_tc_fwd(gyh, wt, None)
             if act:
                 gx = torch.ops.aten.silu_backward(gx, xh)
             gx = gx.permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             gw = conv2d_tc_wgrad(xh, gyh, kh, kw, act=act).permute(0, 3, 1, 2)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0):
+def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=None):
     """add + alpha * F.conv2d(act(x), w, b) on NCHW views of channels_last tensors (act: None or "swish"; add: None or a
     tensor like the result), with the fast bias gradient, in the precision selected by set_conv_precision() (and, for
     "3xtf32", the implementation of set_conv_impl()): the ResNet node of res.py:613-633 and the block's
-    shortcut + 0.1 * node of res.py:273-286.  The tcgen05 kernels take the activation inside (conv(swish(x)) is ONE kernel);
+    shortcut + 0.1 * node of res.py:273-286.  wt: optional [Cin,kh,kw,Cout] davi_conv2d_wt image of w that the caller
+    keeps up to date (the trainer: one batched launch per step); without it the input gradient computes its own.  The tcgen05 kernels take the activation inside (conv(swish(x)) is ONE kernel);
     residual and scale stay elementwise torch operations everywhere (fusing them into the convolution's epilogue was
     measured and dropped, see _ConvTC)."""
     _require_cuda(x, w, b)
@@ -935,7 +939,7 @@ def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0):
         raise ValueError(f"conv2d_bias: activation {act!r} cannot be fused (None or 'swish')")
     if _conv_precision == "3xtf32" and _conv_impl == "tcgen05":
         if conv_tc_supported(x, w, stride, padding):
-            y = _ConvTC.apply(x, w, b, 1 if act else 0)
+            y = _ConvTC.apply(x, w, b, 1 if act else 0, wt)
             return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
         # channel counts that are not 16-byte multiples (the 138-channel pre/post-processing cells, the 3-channel
         # stem, the 50-channel output head): zero-pad the channel axes, run the same kernels, slice the result
@@ -947,7 +951,7 @@ def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0):
             xp = F.pad(x.permute(0, 2, 3, 1), (0, pi)).permute(0, 3, 1, 2)
             wp = F.pad(w.permute(0, 2, 3, 1), (0, pi, 0, 0, 0, 0, 0, po)).permute(0, 3, 1, 2)
             bp = None if b is None else F.pad(b, (0, po))
-            y = _ConvTC.apply(xp, wp, bp, 1 if act else 0)[:, :w.shape[0]]
+            y = _ConvTC.apply(xp, wp, bp, 1 if act else 0, None)[:, :w.shape[0]]
             return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
     if act:
         x = torch.nn.functional.silu(x)

@@ -212,6 +212,8 @@ class FlatState:
             woff += pad(o * cols)
         self.W = torch.zeros(woff, device=device)
         self.dW = torch.zeros(woff, device=device)
+        self.Wt = torch.zeros(woff, device=device)       # transposed + flipped kernels (input gradients), same offsets
+        wt_entries = []                                  # (offset, Cout, taps, Cin) per kernel as the convolutions see it
         where = {id(m): (off, o, i, h, w) for m, off, o, i, h, w in sizes}
         # the q | k | v projections of a nonlocal block are ONE 1x1 convolution: when their three
         # effective kernels are adjacent in W (no alignment gap), the block reads them as one leaf
@@ -232,6 +234,8 @@ class FlatState:
             wv = self.W[oq:oq + rows * C].view(rows, 1, 1, C).permute(0, 3, 1, 2)
             wv.requires_grad_(True)
             blk._qkv_w_override = wv
+            blk._qkv_wt_override = self.Wt[oq:oq + rows * C].view(C, 1, 1, rows)
+            wt_entries.append((oq, rows, 1, C))
             self.slots.append((wv, "dW", oq, rows * C, True))
             self.qkv_blocks.append(blk)
             fused.update(id(c) for c in trio)
@@ -242,11 +246,21 @@ class FlatState:
             wv = self.W[off:off + n].view(o, h, w, i).permute(0, 3, 1, 2)       # OHWI memory = channels_last
             wv.requires_grad_(True)
             m._w_override = wv
+            m._wt_override = self.Wt[off:off + n].view(i, h, w, o)
+            wt_entries.append((off, o, h * w, i))
             self.slots.append((wv, "dW", off, n, True))
         t64 = lambda v: torch.tensor(v, dtype=torch.int64, device=device)
         self.wn_tables = (t64(rv), t64(rg), t64(rw), torch.tensor(rc, dtype=torch.int32, device=device))
         self.wn_rows = len(rv)
         self.wn_modules = [s[0] for s in sizes]
+        # device tables of davi_conv2d_wt_batched: one launch per step refreshes every transposed kernel
+        prefix, tiles = [], 0
+        for _, o, taps, i in wt_entries:
+            prefix.append(tiles)
+            tiles += taps * (-(-o // 32)) * (-(-i // 32))
+        t32 = lambda v: torch.tensor(v, dtype=torch.int32, device=device)
+        self.wt_tables = (t64([e[0] for e in wt_entries]), t32([e[1] for e in wt_entries]), t32([e[2] for e in wt_entries]),
+                          t32([e[3] for e in wt_entries]), t64(prefix + [tiles]), len(wt_entries), tiles)
 
     def clear_grads(self):
         for t, _, _, _, _ in self.slots:
@@ -321,8 +335,10 @@ class FlatState:
         """Detach the model from the fused weight-norm path (it computes its kernels itself again)."""
         for m in getattr(self, "wn_modules", []):
             m._w_override = None
+            m._wt_override = None
         for blk in getattr(self, "qkv_blocks", []):
             blk._qkv_w_override = None
+            blk._qkv_wt_override = None
         self.wn_rows = 0
 
 
@@ -430,6 +446,9 @@ class Trainer:
             rv, rg, rw, rc = st.wn_tables
             _lib.call("davi_weight_norm_fwd", st.P.data_ptr(), st.W.data_ptr(), rv.data_ptr(), rg.data_ptr(),
                       rw.data_ptr(), rc.data_ptr(), st.wn_rows, stream)
+            to, tc, tt, ti, tp, cnt, tiles = st.wt_tables                     # W -> Wt for every input gradient of the step
+            _lib.call("davi_conv2d_wt_batched", st.W.data_ptr(), st.Wt.data_ptr(), to.data_ptr(), tc.data_ptr(),
+                      tt.data_ptr(), ti.data_ptr(), tp.data_ptr(), cnt, tiles, stream)
         nll, kl, nelbo = self.model(x, True, eps, noise)
         global_batch = x.shape[0] * self.world                       # tr.py:174
         loss = (nll.sum() + self.beta_dev * kl.sum()) * (1.0 / global_batch)

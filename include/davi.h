@@ -428,6 +428,13 @@ int davi_conv2d_wgrad_ex(const float* x, const float* gy, float* gw,
                          void* workspace, size_t workspace_bytes, davi_stream_t stream);
 /* wt[ci][taps-1-tap][co] = w[co][tap][ci] (taps = kh*kw): the weights of the input-gradient convolution */
 int davi_conv2d_wt(const float* w, float* wt, int Cout, int taps, int Cin, davi_stream_t stream);
+/* The same for `count` kernels in ONE launch (a trainer calls it once per step, after davi_weight_norm_fwd): kernel i
+ * lives at w_flat + offs[i], its transpose goes to wt_flat + offs[i]; couts / taps / cins give its shape.  DEVICE
+ * tables; tile_prefix[i] = sum over j < i of taps[j] * ceil(couts[j] / 32) * ceil(cins[j] / 32), total_tiles = the
+ * full sum (the grid size). */
+int davi_conv2d_wt_batched(const float* w_flat, float* wt_flat, const int64_t* offs, const int* couts,
+                           const int* taps, const int* cins, const int64_t* tile_prefix, int count,
+                           int64_t total_tiles, davi_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,47 @@ def test_fused_weight_norm_matches_per_layer_path(cuda, convs):
     assert err < 1e-4, err.item()
 
 
+def test_batched_kernel_transpose_matches_the_per_kernel_entry_point(cuda, convs):
+    """davi_conv2d_wt_batched (one launch per training step for every convolution's input-gradient weights) against
+    davi_conv2d_wt per kernel and against the index rule wt[ci][taps-1-tap][co] = w[co][tap][ci] itself: bit-exact
+    (pure data movement), for every weight-normed convolution and every packed q|k|v projection of the model."""
+    from deep_attentive_vi_b200 import _lib
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    from deep_attentive_vi_b200.util.trainer import Trainer
+    kw = parse_flags(**helpers.SMALL_CIFAR)
+    B = 2
+    x = helpers.synthetic_images(kw, B, seed=5).to(cuda)
+    torch.manual_seed(0)
+    m = DeepVAE(**kw)
+    helpers.randomize_zero_init_scalars(m)
+    m = m.to(cuda)
+    tr = Trainer(m, device=cuda)
+    st = tr.state
+    assert st.wt_tables[5] > 0 and len(st.qkv_blocks) > 0
+    st.Wt.fill_(float("nan"))
+    tr.forward_backward(x)                                        # fills W, then Wt, before the forward pass
+    stream = torch.cuda.current_stream().cuda_stream
+    views = [(mod._w_override, mod._wt_override) for mod in st.wn_modules if mod._w_override is not None]
+    views += [(blk._qkv_w_override, blk._qkv_wt_override) for blk in st.qkv_blocks]
+    assert len(views) == st.wt_tables[5]
+    for w, wt in views:
+        wh = w.detach().permute(0, 2, 3, 1)                        # [Cout,kh,kw,Cin] memory
+        assert wh.is_contiguous() and wt.is_contiguous()
+        co, kh, kw_, ci = wh.shape
+        assert tuple(wt.shape) == (ci, kh, kw_, co)
+        want = wh.flip(1, 2).permute(3, 1, 2, 0).contiguous()
+        assert torch.equal(wt, want)
+        single = torch.empty_like(want)
+        _lib.call("davi_conv2d_wt", wh.data_ptr(), single.data_ptr(), co, kh * kw_, ci, stream)
+        assert torch.equal(single, want)
+    # padding between kernels in the flat array is never written
+    covered = torch.zeros_like(st.Wt, dtype=torch.bool)
+    for _, wt in views:
+        off = (wt.data_ptr() - st.Wt.data_ptr()) // 4
+        covered[off:off + wt.numel()] = True
+    assert torch.isnan(st.Wt[~covered]).all()
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_bucketed_gradient_exchange_equals_the_single_exchange(cuda, use_graph):
     """The bucketed path (gradients gathered, weight-norm chain rule finished and the bucket's all-reduce started
