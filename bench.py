@@ -356,8 +356,14 @@ def conv_roofline(trace, device):
         w = torch.randn(Cout, kh, kw, Cin, device=device) * 0.05
         b = torch.randn(Cout, device=device)
 
+        w_lo = torch.empty_like(w)
+        _lib.call("davi_tf32_lo", w.data_ptr(), w_lo.data_ptr(), w.numel(), stream)
+
         def run(i):
-            if kind == "fwd":
+            if kind == "fwd_pre":        # the trainer's convolutions: lo image of the weights kept per step, loaded by TMA
+                _lib.call("davi_conv2d_fwd_pre", x[i].data_ptr(), w.data_ptr(), w_lo.data_ptr(), b.data_ptr(), y[i].data_ptr(),
+                          B, H, W, Cin, Cout, kh, kw, Cin, Cout, 0, ws.data_ptr(), wsb, stream)
+            elif kind == "fwd":
                 _lib.call("davi_conv2d_fwd", x[i].data_ptr(), w.data_ptr(), b.data_ptr(), y[i].data_ptr(), B, H, W, Cin,
                           Cout, kh, kw, Cin, Cout, ws.data_ptr(), wsb, stream)
             else:
@@ -505,6 +511,7 @@ def run_davi(args):
     world, rank, local, device = dist_setup()
     if args.conv_sm_reserve >= 0:
         _lib.set_option(_lib.OPT_CONV_SM_RESERVE, args.conv_sm_reserve)
+    ops.conv_pre_lo = not args.no_pre_lo
     wl = TRAIN_WORKLOADS[args.workload]
     flags = getattr(M, wl["flags"])
     B = args.batch or wl["batch"]
@@ -596,6 +603,8 @@ def run_davi(args):
     e2e_val = B * world * args.steps / (ms_e2e / 1e3)
     cfg = train_config(wl, B, world)
     cfg.update({"params": nparams, "cuda_graph": not args.eager, "convs": CONV_NOTE[args.convs],
+                "weights_lo_image": "once per step (davi_tf32_lo over all kernels, loaded by TMA)" if ops.conv_pre_lo else
+                                    "derived on chip from every staged weight tile",
                 "l2": "inputs (2 GB activations per step) exceed L2; the stand-alone roofline launches rotate over "
                       "operand sets with a total footprint > 3x L2 (every launch reads cold inputs)"})
     line = {
@@ -882,6 +891,8 @@ def main():
     ap.add_argument("--fp32-convs", action="store_true", help="same as --convs fp32")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-pre-lo", action="store_true",
+                    help="A/B: the convolutions derive the lo image of the weights on chip instead of loading the per-step one")
     ap.add_argument("--conv-sm-reserve", type=int, default=-1,
                     help="SMs the convolution grids leave free for the NCCL kernels of the overlapped gradient exchange "
                          "(-1 = the trainer's default: 0 on one GPU)")

@@ -59,6 +59,8 @@ SIGNATURES = {
     "davi_conv2d_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "davi_conv2d_fwd": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _f, _z, _s]),
     "davi_conv2d_fwd_ex": (_i, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _i, _f, _z, _s]),
+    "davi_tf32_lo": (_i, [_f, _f, _l, _s]),
+    "davi_conv2d_fwd_pre": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _i, _f, _z, _s]),
     "davi_conv2d_wgrad_ex": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _i, _f, _z, _s]),
     "davi_conv2d_wgrad": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _f, _z, _s]),
     "davi_conv2d_wt": (_i, [_f, _f, _i, _i, _i, _s]),

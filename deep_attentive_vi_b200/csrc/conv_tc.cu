@@ -87,6 +87,8 @@ struct CvGeom {
     int stages, slots;          // hi ring (TMA targets: A | B); lo ring: B lo image in smem + A hi|lo in TMEM
     int tile_ok;                // the staged [128 x Cout] output tile fits the operand rings
     int reduce;                 // 1: every segment is written to the workspace, conv_reduce_kernel sums them
+    int blo;                    // MODE 0: 1 = the lo image of B comes from memory (davi_tf32_lo of the weights, loaded by
+                                //   TMA straight into the lo ring) instead of the lo warps' shared -> shared pass
     int debug;                  // DAVI_OPT_CONV_DEBUG bits (profiling only): 1 no lo arithmetic, 2 one MMA of three, 4 no stores
     // convolution
     int H, W, Cin, Cout, kh, kw, pt, pl, taps, cch, last_ksteps;
@@ -262,7 +264,8 @@ template <int MODE, int ACT>
 // (14 warps: 4 + 4 + 3 + 3 per SM sub-partition of 16 K registers -> at most 128 registers per thread)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmB1, const CvArgs a, const CvGeom g) {
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmL,
+                 const __grid_constant__ CUtensorMap tmL1, const CvArgs a, const CvGeom g) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ CvBars bars;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -297,6 +300,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmB1);
+        tma_prefetch_desc(&tmL);
+        tma_prefetch_desc(&tmL1);
     }
     if (warp == 13) cv_tmem_alloc2(&bars.tmem_base, 512);  // the same warp of BOTH CTAs
     tc_fence_before();
@@ -514,7 +519,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // B: lo image, shared -> shared (same swizzled offsets)
                 const float4* __restrict__ src = reinterpret_cast<const float4*>(sB(s));
                 float4* __restrict__ dst = reinterpret_cast<float4*>(sLo(l));
-                int i = (g.debug & 1) ? n16 : lt;
+                int i = ((g.debug & 1) || g.blo) ? n16 : lt;               // blo: TMA delivered the lo image already
                 for (; i + 384 < n16; i += 512) {
                     const float4 v0 = src[i], v1 = src[i + 128], v2 = src[i + 256], v3 = src[i + 384];
                     dst[i] = lo4_tf32(v0);
@@ -547,6 +552,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kc = sg.k0; kc < sg.k1; ++kc, ++it) {
                     const int s = it % g.stages;
                     if (it >= (uint32_t)g.stages) mbar_wait(&bars.empty[s], ((it / g.stages) - 1) & 1);
+                    // precomputed lo image of B: it lands in lo slot l with the stage's barrier, so the slot must have
+                    // been released by the MMAs of its previous use (the lo warps wait for the same phase before they
+                    // overwrite the slot's TMEM half)
+                    const int l = it % g.slots;
+                    const bool blo = MODE == 0 && g.blo;
+                    if (blo && it >= (uint32_t)g.slots) mbar_wait(&bars.lo_free[l], ((it / g.slots) - 1) & 1);
                     CV_STAMP(0, it);
                     if (MODE == 0) {
                         const int tap = kc / g.cch, cc = kc - tap * g.cch;
@@ -554,11 +565,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int img = sg.tile / g.tiles_per_image;
                         const int y0 = (sg.tile - img * g.tiles_per_image) * 2 * g.rows_cta + (int)rank * g.rows_cta;
                         const bool la = !(g.debug & 16), lb = !(g.debug & 32);
-                        mbar_expect_tx(&bars.full[s], (la ? kCvABytes : 0) + (lb ? b_bytes : 0));
+                        mbar_expect_tx(&bars.full[s], (la ? kCvABytes : 0) + (lb ? (blo ? 2 * b_bytes : b_bytes) : 0));
                         if (la) cv_tma_4d(sA(s), &tmA, cc * 32, tx - g.pl, y0 + ty - g.pt, img, &bars.full[s]);
                         if (lb) tma_load_3d(sB(s), &tmB, cc * 32, tap, (int)rank * nbp0, &bars.full[s]);
                         if (lb && nbp1 > 0)
                             tma_load_3d(sB(s) + nbp0 * 128, &tmB1, cc * 32, tap, g.np0 + (int)rank * nbp1, &bars.full[s]);
+                        if (lb && blo) {
+                            tma_load_3d(sLo(l), &tmL, cc * 32, tap, (int)rank * nbp0, &bars.full[s]);
+                            if (nbp1 > 0)
+                                tma_load_3d(sLo(l) + nbp0 * 128, &tmL1, cc * 32, tap, g.np0 + (int)rank * nbp1, &bars.full[s]);
+                        }
                     } else {
                         const int img = kc / g.chunks_per_image;
                         const int y0 = (kc - img * g.chunks_per_image) * g.chunk_rows;
@@ -719,6 +735,25 @@ __global__ void conv_wt_batched_kernel(const float* __restrict__ w_flat, float* 
     }
 }
 
+// dst = lo part of the 3xTF32 split of src (tc_common.cuh lo_tf32: v = trunc_tf32(v) + lo, lo rounded to tf32) -- exactly
+// what the lo warps compute from a landed B tile; a trainer runs it once per step over all its kernels and their
+// transposes and hands the image to davi_conv2d_fwd_pre (bit-identical results, no shared -> shared pass per chunk).
+__global__ void __launch_bounds__(256) tf32_lo_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;
+    const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
+    float4* __restrict__ d4 = reinterpret_cast<float4*>(dst);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 v0 = __ldcs(s4 + i), v1 = __ldcs(s4 + i + stride), v2 = __ldcs(s4 + i + 2 * stride), v3 = __ldcs(s4 + i + 3 * stride);
+        d4[i] = lo4_tf32(v0);
+        d4[i + stride] = lo4_tf32(v1);
+        d4[i + 2 * stride] = lo4_tf32(v2);
+        d4[i + 3 * stride] = lo4_tf32(v3);
+    }
+    for (; i < n4; i += stride) d4[i] = lo4_tf32(__ldcs(s4 + i));
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = lo_tf32(src[(n4 << 2) + threadIdx.x]);
+}
+
 // Weight gradients with few tiles and a long pixel axis (1x1 kernels: 2 tiles x 320 chunks) are cut into dozens of
 // segments per tile; one owner adding them serially would take longer than the MMAs.  In `reduce` mode every
 // segment lands in the workspace and this kernel sums the segments of a tile in pair order (deterministic).
@@ -844,8 +879,8 @@ size_t conv_tc_workspace_bytes() {
 }
 
 template <int MODE>
-static int cv_launch(const char* fn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, CvArgs a,
-                     const CvGeom& g,
+static int cv_launch(const char* fn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1,
+                     const CUtensorMap& tmL, const CUtensorMap& tmL1, CvArgs a, const CvGeom& g,
                      void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const size_t n_pad = (size_t)(g.n_total + 31) / 32 * 32;
     const size_t need = (size_t)kCvFlagBytes + (size_t)g.pairs * (g.reduce ? 2 : 1) * 2 * 128 * n_pad * 4;
@@ -858,10 +893,10 @@ static int cv_launch(const char* fn, const CUtensorMap& tmA, const CUtensorMap& 
     const size_t smem = 1024 + (size_t)g.stages * (kCvABytes + g.nb * 128) + (size_t)g.slots * g.nb * 128 + kCvStageBytes;
     if (a.act) {
         DAVI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_gemm_kernel<MODE, 1><<<2 * g.pairs, kCvThreads, smem, st>>>(tmA, tmB, tmB1, a, g);
+        conv_gemm_kernel<MODE, 1><<<2 * g.pairs, kCvThreads, smem, st>>>(tmA, tmB, tmB1, tmL, tmL1, a, g);
     } else {
         DAVI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_gemm_kernel<MODE, 0><<<2 * g.pairs, kCvThreads, smem, st>>>(tmA, tmB, tmB1, a, g);
+        conv_gemm_kernel<MODE, 0><<<2 * g.pairs, kCvThreads, smem, st>>>(tmA, tmB, tmB1, tmL, tmL1, a, g);
     }
     int rc = check_launch(fn);
     if (rc || !g.reduce) return rc;
@@ -891,8 +926,8 @@ static bool cv_geom(CvGeom& g, int mode, int B, int H, int W, int Cin, int Cout,
     return cv_finish(g, sms);
 }
 
-int conv_fwd_tc_launch(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
-                       int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, int act, void* workspace,
+int conv_fwd_tc_launch(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int B, int H,
+                       int W, int Cin, int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, int act, void* workspace,
                        size_t workspace_bytes, cudaStream_t st) {
     CvGeom g{};
     if (!cv_geom(g, 0, B, H, W, Cin, Cout, kh, kw, cv_sms())) {
@@ -900,7 +935,8 @@ int conv_fwd_tc_launch(const float* x, const float* w, const float* bias, float*
         return DAVI_EINVAL;
     }
     g.out_sp = y_sp;
-    CUtensorMap tmA, tmB, tmB1;
+    g.blo = w_lo ? 1 : 0;
+    CUtensorMap tmA, tmB, tmB1, tmL, tmL1;
     int rc;
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -915,11 +951,17 @@ int conv_fwd_tc_launch(const float* x, const float* w, const float* bias, float*
         const uint32_t box1[3] = {32, 1, (uint32_t)(g.np1 > 0 ? g.np1 / 2 : g.np0 / 2)};
         if ((rc = make_tmap_nd(&tmB, w, 3, dims, str, box, 0))) return rc;
         if ((rc = make_tmap_nd(&tmB1, w, 3, dims, str, box1, 0))) return rc;
+        tmL = tmB;
+        tmL1 = tmB1;
+        if (w_lo) {                                            // same boxes over the precomputed lo image
+            if ((rc = make_tmap_nd(&tmL, w_lo, 3, dims, str, box, 0))) return rc;
+            if ((rc = make_tmap_nd(&tmL1, w_lo, 3, dims, str, box1, 0))) return rc;
+        }
     }
     CvArgs a{};
     a.bias = bias; a.out = y;
     a.act = act;
-    return cv_launch<0>("davi_conv2d_fwd", tmA, tmB, tmB1, a, g, workspace, workspace_bytes, st);
+    return cv_launch<0>("davi_conv2d_fwd", tmA, tmB, tmB1, tmL, tmL1, a, g, workspace, workspace_bytes, st);
 }
 
 int conv_wgrad_tc_launch(const float* x, const float* gy, float* gw, int B, int H, int W, int Cin, int Cout, int kh,
@@ -946,7 +988,7 @@ int conv_wgrad_tc_launch(const float* x, const float* gy, float* gw, int B, int 
     CvArgs a{};
     a.out = gw;
     a.act = act;
-    return cv_launch<1>("davi_conv2d_wgrad", tmA, tmB, tmB, a, g, workspace, workspace_bytes, st);
+    return cv_launch<1>("davi_conv2d_wgrad", tmA, tmB, tmB, tmB, tmB, a, g, workspace, workspace_bytes, st);
 }
 
 // plan[0..11] = tiles, k-chunks per tile, CTA pairs, accumulator columns, columns of MMA 0, of MMA 1, hi-ring stages,
@@ -1015,8 +1057,30 @@ extern "C" int davi_conv2d_fwd_ex(const float* x, const float* w, const float* b
     DAVI_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && (!bias || aligned16(bias)), "alignment");
     DAVI_REQUIRE(mult4(x_sp) && mult4(y_sp) && x_sp >= Cin && y_sp >= Cout, "pixel strides");
     DAVI_REQUIRE(act == 0 || act == 1, "act");
-    return conv_fwd_tc_launch(x, w, bias, y, B, H, W, Cin, Cout, kh, kw, x_sp, y_sp, act, workspace, workspace_bytes,
+    return conv_fwd_tc_launch(x, w, nullptr, bias, y, B, H, W, Cin, Cout, kh, kw, x_sp, y_sp, act, workspace, workspace_bytes,
                               (cudaStream_t)stream);
+}
+
+extern "C" int davi_conv2d_fwd_pre(const float* x, const float* w, const float* w_lo, const float* bias, float* y, int B,
+                                   int H, int W, int Cin, int Cout, int kh, int kw, int64_t x_sp, int64_t y_sp, int act,
+                                   void* workspace, size_t workspace_bytes, davi_stream_t stream) {
+    DAVI_REQUIRE(x && w && w_lo && y && w_lo != w, "null / aliased pointer");
+    DAVI_REQUIRE(aligned16(x) && aligned16(w) && aligned16(w_lo) && aligned16(y) && (!bias || aligned16(bias)), "alignment");
+    DAVI_REQUIRE(mult4(x_sp) && mult4(y_sp) && x_sp >= Cin && y_sp >= Cout, "pixel strides");
+    DAVI_REQUIRE(act == 0 || act == 1, "act");
+    return conv_fwd_tc_launch(x, w, w_lo, bias, y, B, H, W, Cin, Cout, kh, kw, x_sp, y_sp, act, workspace, workspace_bytes,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int davi_tf32_lo(const float* src, float* dst, int64_t n, davi_stream_t stream) {
+    DAVI_REQUIRE(src && dst && src != dst && n >= 0, "null / aliased pointer, negative size");
+    DAVI_REQUIRE(aligned16(src) && aligned16(dst), "alignment");
+    if (n == 0) return DAVI_OK;
+    int64_t blocks = (n / 4 + 4 * 256 - 1) / (4 * 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tf32_lo_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    return check_launch("davi_tf32_lo");
 }
 
 extern "C" int davi_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,

@@ -113,13 +113,15 @@ class NonlocalResNetBlock(nn.Module):
         # set by util/trainer.py: one leaf view [2d+C, C, 1, 1] over the three adjacent effective kernels
         self._qkv_w_override = None
         self._qkv_wt_override = None
+        self._qkv_lo_override = None
 
     def _qkv(self, x):
         d, C, pad = self._key_dim, self._C, self._pad
         bs = [self.query_conv.bias, self.key_conv.bias, self.value_conv.bias]
         if self._qkv_w_override is not None:
             b = torch.cat(bs, 0) if bs[0] is not None else None
-            return to_nhwc(ops.conv2d_bias(to_nchw(x), self._qkv_w_override, b, wt=self._qkv_wt_override))
+            return to_nhwc(ops.conv2d_bias(to_nchw(x), self._qkv_w_override, b, wt=self._qkv_wt_override,
+                                           lo=self._qkv_lo_override))
         ws = [self.query_conv.kernel(), self.key_conv.kernel(), self.value_conv.kernel()]
         if pad:   # keep rows 16-byte multiples (C = 138 in the CIFAR-10 pre-processor)
             ws.append(ws[0].new_zeros(pad, C, 1, 1))

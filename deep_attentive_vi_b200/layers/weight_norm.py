@@ -43,6 +43,7 @@ class WNConv2d(nn.Module):
         # kernel (davi_weight_norm_fwd) fills for all convolutions of the model before the forward
         self._w_override = None
         self._wt_override = None    # likewise: [Cin,kh,kw,Cout] transposed + flipped image of the kernel (input gradient)
+        self._lo_override = None    # likewise: (davi_tf32_lo image of the kernel [Cout,kh,kw,Cin], of its transposed image)
 
     def kernel(self):
         if not self.use_weight_norm:
@@ -61,6 +62,7 @@ class WNConv2d(nn.Module):
         k, s = self.k, self.strides
         addc = None if add is None else to_nchw(add)
         wt = self._wt_override if (self.use_weight_norm and self._w_override is not None) else None
+        lo = self._lo_override if wt is not None else None
         if self.padding == "same":
             H, W = x.shape[1], x.shape[2]
             # TF 'same': total = max((ceil(n/s)-1)*s + k - n, 0); before = total//2, rest after
@@ -71,7 +73,7 @@ class WNConv2d(nn.Module):
             (pt, pb), (pl, pr) = pads(H), pads(W)
             if pt == pb and pl == pr:
                 y = ops.conv2d_bias(xc, self.kernel(), self.bias, stride=s, padding=(pt, pl), act=act, add=addc, alpha=alpha,
-                                    wt=wt)
+                                    wt=wt, lo=lo)
             else:
                 if act == "swish":
                     xc = F.silu(xc)

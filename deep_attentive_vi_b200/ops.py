@@ -814,7 +814,8 @@ class _ConvBias3x(torch.autograd.Function):
 #   "cudnn"              one cuDNN TF32 call per conv / dgrad / wgrad over a tripled contraction axis (_ConvBias3x)
 CONV_IMPLS = ("tcgen05", "cudnn")
 _conv_impl = "tcgen05"
-conv_trace = None      # measurement hook (bench.py): a list collects ("fwd" | "wgrad", B, H, W, Cin, Cout, kh, kw) per launch
+conv_pre_lo = True     # use the caller's davi_tf32_lo images of the weights when it passes them (False: A/B measurements)
+conv_trace = None      # measurement hook (bench.py): a list collects ("fwd" | "fwd_pre" | "wgrad", B, H, W, Cin, Cout, kh, kw) per launch
 _conv_ws = {}          # device index -> zero-initialised workspace of the stream-K split (one per device: the
                        # model's convolutions are issued on one stream at a time)
 
@@ -859,15 +860,22 @@ def conv_tc_supported(x, w, stride, padding):
     return _conv_tc_shape_ok(B, H, W, Cin, Cout, kh, kw, stride, padding)
 
 
-def conv2d_tc_fwd(x, w, b, act=0):
+def conv2d_tc_fwd(x, w, b, act=0, w_lo=None):
     """x [B,H,W,Cin] contiguous, w [Cout,kh,kw,Cin] contiguous (OHWI), b [Cout] or None -> y [B,H,W,Cout]
-    = conv(swish(x) if act else x) + b."""
+    = conv(swish(x) if act else x) + b.  w_lo: optional davi_tf32_lo image of w (same layout) that the caller keeps up
+    to date; the kernel then loads it instead of deriving it from every staged weight tile (same bits out)."""
     B, H, W, Cin = x.shape
     Cout, kh, kw, _ = w.shape
     y = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.float32)
     ws, wsb = _conv_workspace(x.device)
+    pre = w_lo is not None and conv_pre_lo
     if conv_trace is not None:
-        conv_trace.append(("fwd", B, H, W, Cin, Cout, kh, kw))
+        conv_trace.append(("fwd_pre" if pre else "fwd", B, H, W, Cin, Cout, kh, kw))
+    if pre:
+        assert w_lo.shape == w.shape and w_lo.is_contiguous()
+        _lib_call("davi_conv2d_fwd_pre", _p(x), _p(w), _p(w_lo), _p(b), _p(y), B, H, W, Cin, Cout, kh, kw, Cin, Cout, int(act),
+                  _p(ws), wsb, _stream())
+        return y
     _lib_call("davi_conv2d_fwd_ex", _p(x), _p(w), _p(b), _p(y), B, H, W, Cin, Cout, kh, kw, Cin, Cout, int(act), _p(ws), wsb,
               _stream())
     return y
@@ -896,12 +904,13 @@ class _ConvTC(torch.autograd.Function):
     davi_colsum.  Saves x and w themselves -- no split copies."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, wt):
+    def forward(ctx, x, w, b, act, wt, lo):
         xh, wh = _nhwc(x), _nhwc(w)
         ctx.save_for_backward(xh, wh)
         ctx.act = int(act)
         ctx.wt = wt         # [Cin,kh,kw,Cout]: the trainer's per-step davi_conv2d_wt_batched image of w, or None
-        return conv2d_tc_fwd(xh, wh, b, act=act).permute(0, 3, 1, 2)
+        w_lo, ctx.wt_lo = lo if lo is not None else (None, None)      # davi_tf32_lo images of w and wt (trainer), or None
+        return conv2d_tc_fwd(xh, wh, b, act=act, w_lo=w_lo).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gy):
@@ -913,25 +922,27 @@ class _ConvTC(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             gb = colsum_nhwc(gy)                                   # first: gy is still L2-resident
         if ctx.needs_input_grad[0]:
-            wt = ctx.wt
+            wt, wt_lo = ctx.wt, ctx.wt_lo
             if wt is None:
-                wt = torch.empty((Cin, kh, kw, Cout), device=wh.device, dtype=torch.float32)
+                wt, wt_lo = torch.empty((Cin, kh, kw, Cout), device=wh.device, dtype=torch.float32), None
                 _lib_call("davi_conv2d_wt", _p(wh), _p(wt), Cout, kh * kw, Cin, _stream())
-            gx = conv2d_tc_fwd(gyh, wt, None)
+            gx = conv2d_tc_fwd(gyh, wt, None, w_lo=wt_lo)
             if act:
                 gx = torch.ops.aten.silu_backward(gx, xh)
             gx = gx.permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             gw = conv2d_tc_wgrad(xh, gyh, kh, kw, act=act).permute(0, 3, 1, 2)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=None):
+def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=None, lo=None):
     """add + alpha * F.conv2d(act(x), w, b) on NCHW views of channels_last tensors (act: None or "swish"; add: None or a
     tensor like the result), with the fast bias gradient, in the precision selected by set_conv_precision() (and, for
     "3xtf32", the implementation of set_conv_impl()): the ResNet node of res.py:613-633 and the block's
     shortcut + 0.1 * node of res.py:273-286.  wt: optional [Cin,kh,kw,Cout] davi_conv2d_wt image of w that the caller
-    keeps up to date (the trainer: one batched launch per step); without it the input gradient computes its own.  The tcgen05 kernels take the activation inside (conv(swish(x)) is ONE kernel);
+    keeps up to date (the trainer: one batched launch per step); without it the input gradient computes its own.
+    lo: optional (w_lo, wt_lo), the davi_tf32_lo images of w (OHWI memory) and of wt, likewise kept by the caller.
+    The tcgen05 kernels take the activation inside (conv(swish(x)) is ONE kernel);
     residual and scale stay elementwise torch operations everywhere (fusing them into the convolution's epilogue was
     measured and dropped, see _ConvTC)."""
     _require_cuda(x, w, b)
@@ -939,7 +950,7 @@ def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=
         raise ValueError(f"conv2d_bias: activation {act!r} cannot be fused (None or 'swish')")
     if _conv_precision == "3xtf32" and _conv_impl == "tcgen05":
         if conv_tc_supported(x, w, stride, padding):
-            y = _ConvTC.apply(x, w, b, 1 if act else 0, wt)
+            y = _ConvTC.apply(x, w, b, 1 if act else 0, wt, lo if wt is not None else None)
             return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
         # channel counts that are not 16-byte multiples (the 138-channel pre/post-processing cells, the 3-channel
         # stem, the 50-channel output head): zero-pad the channel axes, run the same kernels, slice the result
@@ -951,7 +962,7 @@ def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=
             xp = F.pad(x.permute(0, 2, 3, 1), (0, pi)).permute(0, 3, 1, 2)
             wp = F.pad(w.permute(0, 2, 3, 1), (0, pi, 0, 0, 0, 0, 0, po)).permute(0, 3, 1, 2)
             bp = None if b is None else F.pad(b, (0, po))
-            y = _ConvTC.apply(xp, wp, bp, 1 if act else 0, None)[:, :w.shape[0]]
+            y = _ConvTC.apply(xp, wp, bp, 1 if act else 0, None, None)[:, :w.shape[0]]
             return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
     if act:
         x = torch.nn.functional.silu(x)

@@ -210,9 +210,14 @@ class FlatState:
                 rv.append(v_off + r * cols); rg.append(g_off + r); rw.append(woff + r * cols); rc.append(cols)
             sizes.append((m, woff, o, i, h, w))
             woff += pad(o * cols)
-        self.W = torch.zeros(woff, device=device)
+        # W | Wt: effective kernels and their transposed + flipped images (input gradients, same offsets) in ONE
+        # allocation, so that ONE davi_tf32_lo launch per step writes the lo halves of both (Wlo | Wtlo, same offsets
+        # again): the convolutions load those by TMA instead of deriving them from every weight tile they stage
+        self.WW = torch.zeros(2 * woff, device=device)
+        self.W, self.Wt = self.WW[:woff], self.WW[woff:]
+        self.LL = torch.zeros(2 * woff, device=device)
+        self.Wlo, self.Wtlo = self.LL[:woff], self.LL[woff:]
         self.dW = torch.zeros(woff, device=device)
-        self.Wt = torch.zeros(woff, device=device)       # transposed + flipped kernels (input gradients), same offsets
         wt_entries = []                                  # (offset, Cout, taps, Cin) per kernel as the convolutions see it
         where = {id(m): (off, o, i, h, w) for m, off, o, i, h, w in sizes}
         # the q | k | v projections of a nonlocal block are ONE 1x1 convolution: when their three
@@ -235,6 +240,7 @@ class FlatState:
             wv.requires_grad_(True)
             blk._qkv_w_override = wv
             blk._qkv_wt_override = self.Wt[oq:oq + rows * C].view(C, 1, 1, rows)
+            blk._qkv_lo_override = (self.Wlo[oq:oq + rows * C].view(rows, 1, 1, C), self.Wtlo[oq:oq + rows * C].view(C, 1, 1, rows))
             wt_entries.append((oq, rows, 1, C))
             self.slots.append((wv, "dW", oq, rows * C, True))
             self.qkv_blocks.append(blk)
@@ -247,6 +253,7 @@ class FlatState:
             wv.requires_grad_(True)
             m._w_override = wv
             m._wt_override = self.Wt[off:off + n].view(i, h, w, o)
+            m._lo_override = (self.Wlo[off:off + n].view(o, h, w, i), self.Wtlo[off:off + n].view(i, h, w, o))
             wt_entries.append((off, o, h * w, i))
             self.slots.append((wv, "dW", off, n, True))
         t64 = lambda v: torch.tensor(v, dtype=torch.int64, device=device)
@@ -336,9 +343,11 @@ class FlatState:
         for m in getattr(self, "wn_modules", []):
             m._w_override = None
             m._wt_override = None
+            m._lo_override = None
         for blk in getattr(self, "qkv_blocks", []):
             blk._qkv_w_override = None
             blk._qkv_wt_override = None
+            blk._qkv_lo_override = None
         self.wn_rows = 0
 
 
@@ -449,6 +458,7 @@ class Trainer:
             to, tc, tt, ti, tp, cnt, tiles = st.wt_tables                     # W -> Wt for every input gradient of the step
             _lib.call("davi_conv2d_wt_batched", st.W.data_ptr(), st.Wt.data_ptr(), to.data_ptr(), tc.data_ptr(),
                       tt.data_ptr(), ti.data_ptr(), tp.data_ptr(), cnt, tiles, stream)
+            _lib.call("davi_tf32_lo", st.WW.data_ptr(), st.LL.data_ptr(), st.WW.numel(), stream)   # W | Wt -> Wlo | Wtlo
         nll, kl, nelbo = self.model(x, True, eps, noise)
         global_batch = x.shape[0] * self.world                       # tr.py:174
         loss = (nll.sum() + self.beta_dev * kl.sum()) * (1.0 / global_batch)

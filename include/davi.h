@@ -426,6 +426,16 @@ int davi_conv2d_wgrad_ex(const float* x, const float* gy, float* gw,
                          int B, int H, int W, int Cin, int Cout, int kh, int kw,
                          int64_t x_sp, int64_t gy_sp, int act,
                          void* workspace, size_t workspace_bytes, davi_stream_t stream);
+/* Weights that live across many calls (a trainer's parameters between two optimiser steps): the lo half of their
+ * 3xTF32 split can be computed once -- dst[i] = lo(src[i]), v = trunc_tf32(v) + lo(v), lo rounded to tf32, the value the
+ * kernel otherwise derives from every weight tile it stages -- and handed to the convolution, which then loads it by TMA
+ * beside the weights themselves.  davi_conv2d_fwd_pre(x, w, w_lo = davi_tf32_lo(w), ...) == davi_conv2d_fwd_ex(x, w, ...)
+ * bit for bit; w_lo has the layout of w.  (Input gradient: wt and davi_tf32_lo(wt).) */
+int davi_tf32_lo(const float* src, float* dst, int64_t n, davi_stream_t stream);
+int davi_conv2d_fwd_pre(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                        int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                        int64_t x_sp, int64_t y_sp, int act,
+                        void* workspace, size_t workspace_bytes, davi_stream_t stream);
 /* wt[ci][taps-1-tap][co] = w[co][tap][ci] (taps = kh*kw): the weights of the input-gradient convolution */
 int davi_conv2d_wt(const float* w, float* wt, int Cout, int taps, int Cin, davi_stream_t stream);
 /* The same for `count` kernels in ONE launch (a trainer calls it once per step, after davi_weight_norm_fwd): kernel i

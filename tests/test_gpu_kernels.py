@@ -504,6 +504,57 @@ def test_conv_tcgen05_strided_views_through_the_abi(cuda, libdavi):
     assert int(ws[:256].view(torch.int32).abs().max()) == 0
 
 
+def _tf32_lo_restatement(v):
+    """tc_common.cuh lo_tf32 in integer arithmetic: hi = v with the 13 low mantissa bits cleared (what the tensor core
+    reads of an fp32 pattern), lo = (v - hi) rounded to tf32, nearest, ties away from zero."""
+    hi = (v.view(torch.int32) & -8192).view(torch.float32)
+    r = v - hi                                                     # exact
+    return ((r.view(torch.int32) + 4096) & -8192).view(torch.float32)
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,k", [
+    (3, 16, 16, 64, 64, 3),          # whole tiles per pair
+    (40, 16, 16, 316, 316, 3),       # headline shape: stream-K segments, two MMAs per k-step (256 + 64 columns)
+    (40, 16, 16, 276, 340, 1),       # packed q|k|v projection
+    (2, 32, 32, 140, 140, 3),        # 32-wide maps, last channel chunk of 12
+    (40, 16, 16, 276, 40, 3),        # parameter heads: 64 accumulator columns
+])
+def test_conv_with_precomputed_lo_image_is_bit_identical(cuda, libdavi, B, H, W, ci, co, k):
+    """davi_tf32_lo against its integer restatement (bit-exact), and davi_conv2d_fwd_pre (lo image of the weights
+    loaded by TMA into the lo ring) against davi_conv2d_fwd_ex (lo image derived on chip from every staged tile):
+    the same bits out, with and without the fused swish, twice in a row (ring phases and flags left clean)."""
+    import ctypes
+    from deep_attentive_vi_b200 import _lib
+    torch.manual_seed(ci * 7 + co)
+    x = torch.randn(B, H, W, ci, device=cuda)
+    w = torch.randn(co, k, k, ci, device=cuda) / (ci * k * k) ** 0.5
+    w.view(-1)[:7] = torch.tensor([0.0, 1.0, -1.0, 2.0 ** -20, 1.0 + 2.0 ** -12, 1.0 + 2.0 ** -12 + 2.0 ** -23,
+                                   -(1.0 + 2.0 ** -12 + 2.0 ** -23)], device=cuda)    # exact cases and rounding ties
+    b = torch.randn(co, device=cuda)
+    w_lo = torch.full_like(w, float("nan"))
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.call("davi_tf32_lo", p(w), p(w_lo), w.numel(), st)
+    assert torch.equal(w_lo, _tf32_lo_restatement(w))
+    odd = torch.randn(1027, device=cuda)                           # ragged tail (n % 4 != 0) on a 16-byte aligned base
+    odd_lo = torch.full((1032,), 5.0, device=cuda)
+    _lib.call("davi_tf32_lo", p(odd), p(odd_lo), 1027, st)
+    assert torch.equal(odd_lo[:1027], _tf32_lo_restatement(odd)) and bool((odd_lo[1027:] == 5.0).all())
+    wsb = libdavi.davi_conv2d_workspace_bytes()
+    ws = torch.zeros(wsb // 4, device=cuda)
+    for act in (0, 1):
+        y0 = torch.empty(B, H, W, co, device=cuda)
+        _lib.call("davi_conv2d_fwd_ex", p(x), p(w), p(b), p(y0), B, H, W, ci, co, k, k, ci, co, act, p(ws), wsb, st)
+        for _ in range(2):
+            y1 = torch.full((B, H, W, co), float("nan"), device=cuda)
+            _lib.call("davi_conv2d_fwd_pre", p(x), p(w), p(w_lo), p(b), p(y1), B, H, W, ci, co, k, k, ci, co, act, p(ws),
+                      wsb, st)
+            assert torch.equal(y0, y1), (act, (y0 - y1).abs().max().item())
+    assert int(ws[:256].view(torch.int32).abs().max()) == 0
+    with pytest.raises(_lib.DaviError):                            # the lo image must be a separate array
+        _lib.call("davi_conv2d_fwd_pre", p(x), p(w), p(w), p(b), p(y0), B, H, W, ci, co, k, k, ci, co, 0, p(ws), wsb, st)
+
+
 def test_conv_tcgen05_envelope_and_fallback(cuda):
     """Shapes outside the kernel's envelope: stride 2 and more than 384 channels go through the cuDNN 3xTF32 path;
     channel counts that are not 16-byte multiples (138-channel cells, 3-channel stem, 50-channel head) are zero-padded

@@ -134,12 +134,56 @@ def test_batched_kernel_transpose_matches_the_per_kernel_entry_point(cuda, convs
         single = torch.empty_like(want)
         _lib.call("davi_conv2d_wt", wh.data_ptr(), single.data_ptr(), co, kh * kw_, ci, stream)
         assert torch.equal(single, want)
+    # the lo images of the step (one davi_tf32_lo launch over W | Wt) and the views the layers read them through
+    hi = (st.WW.view(torch.int32) & -8192).view(torch.float32)
+    want_lo = (((st.WW - hi).view(torch.int32) + 4096) & -8192).view(torch.float32)
+    ok = ~torch.isnan(st.WW)
+    assert torch.equal(st.LL[ok], want_lo[ok])
+    los = [mod._lo_override for mod in st.wn_modules if mod._w_override is not None] + [blk._qkv_lo_override for blk in st.qkv_blocks]
+    for (w, wt), (w_lo, wt_lo) in zip(views, los):
+        assert w_lo.data_ptr() - st.Wlo.data_ptr() == w.data_ptr() - st.W.data_ptr() and w_lo.shape == w.permute(0, 2, 3, 1).shape
+        assert wt_lo.data_ptr() - st.Wtlo.data_ptr() == wt.data_ptr() - st.Wt.data_ptr() and wt_lo.shape == wt.shape
     # padding between kernels in the flat array is never written
     covered = torch.zeros_like(st.Wt, dtype=torch.bool)
     for _, wt in views:
         off = (wt.data_ptr() - st.Wt.data_ptr()) // 4
         covered[off:off + wt.numel()] = True
     assert torch.isnan(st.Wt[~covered]).all()
+
+
+def test_step_with_precomputed_lo_images_equals_the_on_chip_path(cuda):
+    """The training step with the per-step lo images of all kernels (davi_conv2d_fwd_pre) against the same step with the
+    lo images derived on chip (ops.conv_pre_lo = False): identical loss terms and an identical flat gradient."""
+    from deep_attentive_vi_b200 import ops
+    from deep_attentive_vi_b200.model import DeepVAE, parse_flags
+    from deep_attentive_vi_b200.util.trainer import Trainer
+    ops.set_conv_precision("3xtf32")
+    ops.set_conv_impl("tcgen05")
+    kw = parse_flags(**helpers.SMALL_CIFAR)
+    B = 4
+    x = helpers.synthetic_images(kw, B, seed=2).to(cuda)
+    torch.manual_seed(0)
+    m = DeepVAE(**kw)
+    helpers.randomize_zero_init_scalars(m)
+    eps, noise = m.draw_noise(B, "cpu", generator=torch.Generator().manual_seed(1), training=True)
+    eps = [e.to(cuda) for e in eps]
+    noise = [None if nz is None else tuple(None if t is None else t.to(cuda) for t in nz) for nz in noise]
+    m = m.to(cuda)
+    tr = Trainer(m, device=cuda)
+    out = []
+    try:
+        for pre in (True, False):
+            ops.conv_pre_lo = pre
+            n0 = ops._lib.launch_count()
+            nll, kl = tr.forward_backward(x, eps, noise)
+            out.append((nll.clone(), kl.clone(), tr.state.G.clone(), ops._lib.launch_count() - n0))
+    finally:
+        ops.conv_pre_lo = True
+    (n1, k1, g1, c1), (n2, k2, g2, c2) = out
+    assert c1 == c2                                               # same launches, other entry point
+    assert torch.allclose(n1, n2, rtol=1e-6) and torch.allclose(k1, k2, rtol=1e-6)
+    err = ((g1 - g2).norm() / g2.norm()).item()
+    assert err < 1e-6, err
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
