@@ -512,6 +512,8 @@ def run_davi(args):
     if args.conv_sm_reserve >= 0:
         _lib.set_option(_lib.OPT_CONV_SM_RESERVE, args.conv_sm_reserve)
     ops.conv_pre_lo = not args.no_pre_lo
+    if args.plain_slices:
+        ops.split_channels_fused = False
     wl = TRAIN_WORKLOADS[args.workload]
     flags = getattr(M, wl["flags"])
     B = args.batch or wl["batch"]
@@ -891,6 +893,9 @@ def main():
     ap.add_argument("--fp32-convs", action="store_true", help="same as --convs fp32")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--plain-slices", action="store_true",
+                    help="A/B: channel splits of the variational layers as plain slices (zero fill + copy + sum per piece on "
+                         "the way back) instead of ops.split_channels (one concatenation)")
     ap.add_argument("--no-pre-lo", action="store_true",
                     help="A/B: the convolutions derive the lo image of the weights on chip instead of loading the per-step one")
     ap.add_argument("--conv-sm-reserve", type=int, default=-1,

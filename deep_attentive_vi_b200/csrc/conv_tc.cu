@@ -935,7 +935,10 @@ int conv_fwd_tc_launch(const float* x, const float* w, const float* w_lo, const 
         return DAVI_EINVAL;
     }
     g.out_sp = y_sp;
-    g.blo = w_lo ? 1 : 0;
+    // the lo image travels through the lo ring, whose depth is the prefetch distance of BOTH weight streams then: with
+    // two slots (more than 320 accumulator columns: the packed q|k|v projections) the on-chip pass is faster (measured
+    // 29.1 vs 31.6 us at 276 -> 340 channels, 1x1), with three the loaded image is (3x3, 316 channels: 89.5 vs 91.4 us)
+    g.blo = (w_lo && g.slots >= 3) ? 1 : 0;
     CUtensorMap tmA, tmB, tmB1, tmL, tmL1;
     int rc;
     {

@@ -130,7 +130,7 @@ class VariationalLayer(nn.Module):
             last = context[-1]
             nv = last.shape[-1] - qd                                                        # vl.py:358
             slots = list(context[:-1])
-            last_values, last_key = last[..., :nv], last[..., nv:]                          # vl.py:359 (views)
+            last_values, last_key = ops.split_channels(last, nv, qd)                        # vl.py:359 (views)
             ctx_in = last_values                                                            # vl.py:360
         new_context = self.compute_context(latent_condition, ctx_in, training, num_samples)
         key = query = None
@@ -139,9 +139,9 @@ class VariationalLayer(nn.Module):
             full = new_context
             g = self._ctx_channels
             if not self._is_last_layer:                                                     # vl.py:375-380
-                new_context, key, query = full[..., :g], full[..., g:g + kd], full[..., g + kd:]
+                new_context, key, query = ops.split_channels(full, g, kd, full.shape[-1] - g - kd)
             else:
-                new_context, query = full[..., :g], full[..., g:]
+                new_context, query = ops.split_channels(full, g, full.shape[-1] - g)
         enc_query = None
         if self._use_encoder_attention:
             enc_query = new_context[..., :self._encoder_attention_hparams.query_dim]        # vl.py:385-386
@@ -175,7 +175,7 @@ class VariationalLayer(nn.Module):
         if self._use_encoder_attention:
             # `condition` = [e[i] tensor, then ("own"/"acc", SharedSlot) for e[i+1..L]]
             f = self._enc_f
-            cond, key0 = condition[0][..., :f], condition[0][..., f:]                       # vl.py:472-473 (views)
+            cond, key0 = ops.split_channels(condition[0], f, condition[0].shape[-1] - f)    # vl.py:472-473 (views)
         else:
             cond = condition
         if not_first:
@@ -183,7 +183,7 @@ class VariationalLayer(nn.Module):
         if self._use_encoder_attention:
             if not_first:
                 f = self._enc_f
-                cond, key0 = cond[..., :f], cond[..., f:]                                   # vl.py:483-494
+                cond, key0 = ops.split_channels(cond, f, cond.shape[-1] - f)                # vl.py:483-494
             att = self._encoder_attention.apply_ctx(enc_query, [("kv", key0, cond)] + list(condition[1:]))  # vl.py:496-499
             if self._enc_ln:
                 cond = ops.ln_gelu_residual(cond, self.cond_ln_gamma, self.cond_ln_beta)    # vl.py:503

@@ -5,6 +5,8 @@ every forward and every gradient below is one or two launches of the hand-
 written sm_100a kernels in ``csrc/`` through ``libdavi.so``.  There is no
 fallback: CPU tensors, a missing library or a failing call raise.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -920,7 +922,7 @@ class _ConvTC(torch.autograd.Function):
         Cout, kh, kw, Cin = wh.shape
         gx = gw = gb = None
         if ctx.needs_input_grad[2]:
-            gb = colsum_nhwc(gy)                                   # first: gy is still L2-resident
+            gb = colsum_nhwc(gyh.permute(0, 3, 1, 2))              # first: gy is still L2-resident (gyh: no second copy)
         if ctx.needs_input_grad[0]:
             wt, wt_lo = ctx.wt, ctx.wt_lo
             if wt is None:
@@ -933,6 +935,49 @@ class _ConvTC(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = conv2d_tc_wgrad(xh, gyh, kh, kw, act=act).permute(0, 3, 1, 2)
         return gx, gw, gb, None, None, None
+
+
+def _scale_add(y, add, alpha):
+    """add + alpha * y (res.py:284-286) as ONE element-wise kernel (torch.add's alpha), not a product and a sum."""
+    if add is None:
+        return y if alpha == 1.0 else alpha * y
+    if isinstance(alpha, (int, float)):
+        return torch.add(add, y, alpha=alpha)
+    return alpha * y + add
+
+
+class _SplitChannels(torch.autograd.Function):
+    """t[..., :s0], t[..., s0:s0+s1], ... as views; the gradient is ONE concatenation of the pieces' gradients.  (Plain
+    slices cost a zero fill and a strided copy per piece plus the sums of the padded pieces on the way back: 8 launches
+    for the three-way split of a decoder cell's output, vl.py:375-380.)"""
+
+    @staticmethod
+    def forward(ctx, t, *sizes):
+        assert sum(sizes) == t.shape[-1]
+        ctx.sizes = sizes
+        outs, c = [], 0
+        for n in sizes:
+            outs.append(t[..., c:c + n])
+            c += n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return (torch.cat(grads, dim=-1),) + (None,) * len(ctx.sizes)
+
+
+split_channels_fused = os.environ.get("DAVI_PLAIN_SLICES", "") != "1"     # False: plain slices (A/B measurements)
+
+
+def split_channels(t, *sizes):
+    """Split the last axis of `t` into consecutive pieces of the given sizes (views, no copy)."""
+    if split_channels_fused and t.requires_grad and torch.is_grad_enabled():
+        return _SplitChannels.apply(t, *sizes)
+    outs, c = [], 0
+    for n in sizes:
+        outs.append(t[..., c:c + n])
+        c += n
+    return tuple(outs)
 
 
 def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=None, lo=None):
@@ -951,7 +996,7 @@ def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=
     if _conv_precision == "3xtf32" and _conv_impl == "tcgen05":
         if conv_tc_supported(x, w, stride, padding):
             y = _ConvTC.apply(x, w, b, 1 if act else 0, wt, lo if wt is not None else None)
-            return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
+            return _scale_add(y, add, alpha)
         # channel counts that are not 16-byte multiples (the 138-channel pre/post-processing cells, the 3-channel
         # stem, the 50-channel output head): zero-pad the channel axes, run the same kernels, slice the result
         # (autograd turns the pads into slices and the slice into a pad on the way back)
@@ -963,11 +1008,11 @@ def conv2d_bias(x, w, b, stride=1, padding=0, act=None, add=None, alpha=1.0, wt=
             wp = F.pad(w.permute(0, 2, 3, 1), (0, pi, 0, 0, 0, 0, 0, po)).permute(0, 3, 1, 2)
             bp = None if b is None else F.pad(b, (0, po))
             y = _ConvTC.apply(xp, wp, bp, 1 if act else 0, None, None)[:, :w.shape[0]]
-            return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
+            return _scale_add(y, add, alpha)
     if act:
         x = torch.nn.functional.silu(x)
     y = _conv2d_plain(x, w, b, stride, padding)
-    return y if add is None and alpha == 1.0 else (alpha * y if add is None else alpha * y + add)
+    return _scale_add(y, add, alpha)
 
 
 def _conv2d_plain(x, w, b, stride, padding):

@@ -430,7 +430,8 @@ int davi_conv2d_wgrad_ex(const float* x, const float* gy, float* gw,
  * 3xTF32 split can be computed once -- dst[i] = lo(src[i]), v = trunc_tf32(v) + lo(v), lo rounded to tf32, the value the
  * kernel otherwise derives from every weight tile it stages -- and handed to the convolution, which then loads it by TMA
  * beside the weights themselves.  davi_conv2d_fwd_pre(x, w, w_lo = davi_tf32_lo(w), ...) == davi_conv2d_fwd_ex(x, w, ...)
- * bit for bit; w_lo has the layout of w.  (Input gradient: wt and davi_tf32_lo(wt).) */
+ * bit for bit; w_lo has the layout of w.  (Input gradient: wt and davi_tf32_lo(wt).)  The kernel takes the image where
+ * that is the faster path (up to 320 output channels: three ring slots) and derives it on chip otherwise. */
 int davi_tf32_lo(const float* src, float* dst, int64_t n, davi_stream_t stream);
 int davi_conv2d_fwd_pre(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
                         int B, int H, int W, int Cin, int Cout, int kh, int kw,

@@ -280,3 +280,36 @@ def test_convolution_launch_plans_of_the_model_shapes(libdavi):
     assert libdavi.davi_conv2d_supported(40, 16, 16, 276, 584, 1, 1) == 0       # more than 384 channels
     assert libdavi.davi_conv2d_plan(0, 40, 16, 16, 276, 584, 1, 1, 148, plan) != 0
     assert libdavi.davi_conv2d_supported(40, 32, 32, 138, 138, 3, 3) == 0       # rows that are not 16-byte multiples
+
+
+def test_split_channels_gradient_is_the_concatenation_of_the_piece_gradients():
+    """ops.split_channels (views out, ONE concatenation on the way back; the channel splits of vl.py:359,375-380,
+    472-473,483-494) against plain slices: same values, same gradient, including an unused piece, a slice of a piece
+    (the encoder query, vl.py:385-386) and a piece that is concatenated again (vl.py:507,547-548)."""
+    import torch
+    from deep_attentive_vi_b200 import ops
+    torch.manual_seed(0)
+    t = torch.randn(2, 3, 3, 10, dtype=torch.float64, requires_grad=True)
+
+    def loss(parts):
+        a, b, c = parts
+        return a.sin().sum() + 2 * (b * b).sum() + (a[..., :2] * c[..., :2]).sum() + torch.cat([a, c * 3], -1).sum()
+
+    keep = ops.split_channels_fused
+    try:
+        grads = []
+        for fused in (True, False):
+            ops.split_channels_fused = fused
+            parts = ops.split_channels(t * 1.0, 5, 2, 3)
+            assert [p.shape[-1] for p in parts] == [5, 2, 3] and all(p._base is not None for p in parts)
+            grads.append(torch.autograd.grad(loss(parts), t)[0])
+        assert torch.equal(grads[0], grads[1])
+        ops.split_channels_fused = True
+        a, b = ops.split_channels(t * 1.0, 4, 6)
+        g, = torch.autograd.grad(a.sum(), t)                         # b unused: its gradient is a zero block
+        assert bool((g[..., :4] == 1).all()) and bool((g[..., 4:] == 0).all())
+        with torch.no_grad():                                        # evaluation: plain views, no autograd node
+            a, b = ops.split_channels(t, 4, 6)
+            assert a.data_ptr() == t.data_ptr() and b.shape[-1] == 6
+    finally:
+        ops.split_channels_fused = keep
