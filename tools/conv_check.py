@@ -81,6 +81,23 @@ def one(kind, B, H, W, Cin, Cout, k):
         wc = wn.contiguous(memory_format=torch.channels_last)
         ops.set_conv_precision("3xtf32")
         res["us_cudnn_3x"] = round(timed(lambda: ops.conv2d_bias(xc, wc, bias, padding=k // 2)), 1)
+    elif kind == "fwd_pre":
+        # the trainer's path: lo image of the weights computed once (davi_tf32_lo), loaded by TMA (davi_conv2d_fwd_pre);
+        # must equal davi_conv2d_fwd_ex bit for bit
+        y, y2 = torch.empty(B, H, W, Cout, device=dev), torch.empty(B, H, W, Cout, device=dev)
+        w_lo = torch.empty_like(w)
+        _lib.call("davi_tf32_lo", p(w), p(w_lo), w.numel(), st)
+        run = lambda: _lib.call("davi_conv2d_fwd_ex", p(x), p(w), p(bias), p(y), B, H, W, Cin, Cout, k, k, Cin, Cout, 0,
+                                p(ws), wsb, st)
+        runp = lambda: _lib.call("davi_conv2d_fwd_pre", p(x), p(w), p(w_lo), p(bias), p(y2), B, H, W, Cin, Cout, k, k, Cin,
+                                 Cout, 0, p(ws), wsb, st)
+        run()
+        runp()
+        torch.cuda.synchronize()
+        res["bit_identical"] = bool(torch.equal(y, y2))
+        res["us"] = round(timed(run), 1)
+        res["us_pre"] = round(timed(runp), 1)
+        res["TFLOPs_pre"] = round(flops / res["us_pre"] * 1e-6, 1)
     else:
         gw = torch.full((Cout, k, k, Cin), float("nan"), device=dev)
         run = lambda: _lib.call("davi_conv2d_wgrad", p(x), p(gy), p(gw), B, H, W, Cin, Cout, k, k, Cin, Cout, p(ws),
