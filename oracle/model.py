@@ -1,8 +1,12 @@
 """CPU oracle of the whole Deep Attentive VAE forward (torch CPU, any dtype).
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED: the
-reference cannot run here; the only published known answers are the
-parameter counts (README.md:32,77,105), checked in tests/test_model_structure.py.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY PINNED: the
+reference's stack cannot be installed here and it publishes no golden vectors, so
+the whole-model [nll, sum kl, nelbo] of three small configurations (train / eval
+mode, one importance-sampled chunk) are pinned to fixtures produced by executing the
+reference's own source on a float64 TensorFlow stand-in (tests/golden/make_golden.py,
+tests/golden/ref_small_*.npz; tests/test_golden.py, 1e-9 relative); the published
+parameter counts (README.md:32,77,105) are checked in tests/test_model_structure.py.
 
 An independent, functional, op-for-op restatement of the reference's model
 (model/vae.py, model/variational_layer.py, model/data_layer.py, layers/resnet.py,

@@ -1,6 +1,9 @@
 """Op-for-op CPU restatement of the reference hot-path functions (torch CPU).
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  PARITY PINNED: the reference ships no
+golden vectors, so the pins are fixtures produced by executing the reference's own source files on
+a float64 TensorFlow stand-in (tests/golden/make_golden.py -> tests/golden/*.npz); tests/test_golden.py
+holds every function below to them at 1e-10.
 
 Every function follows the cited reference lines literally, including the
 transposes / stacks / reshapes the reference materialises, so that (a) autograd

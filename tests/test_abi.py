@@ -78,6 +78,27 @@ def test_validation_rejects_bad_shapes(libdavi):
     assert rc == -2  # DAVI_EWORKSPACE
 
 
+def test_weight_image_entry_points_validate_before_touching_the_device(libdavi):
+    """davi_tf32_lo / davi_conv2d_fwd_pre / davi_conv2d_wt_batched: null, aliased or misaligned arrays and bad
+    activation codes are refused with DAVI_EINVAL (-1) and a message; an empty array is a no-op."""
+    a, b, odd = ctypes.c_void_p(1024), ctypes.c_void_p(2048), ctypes.c_void_p(1028)
+    assert libdavi.davi_tf32_lo(a, a, 16, None) == -1              # in place: the lo image is a separate array
+    assert libdavi.davi_tf32_lo(a, None, 16, None) == -1
+    assert libdavi.davi_tf32_lo(a, odd, 16, None) == -1            # 16-byte alignment
+    assert libdavi.davi_tf32_lo(a, b, -1, None) == -1
+    assert libdavi.davi_tf32_lo(a, b, 0, None) == 0                # nothing to do, nothing launched
+    conv = lambda w_lo, act=0: libdavi.davi_conv2d_fwd_pre(a, b, w_lo, None, a, 1, 16, 16, 32, 32, 3, 3, 32, 32, act,
+                                                           a, 1 << 20, None)
+    assert conv(b) == -1                                           # w_lo must not alias w
+    assert conv(None) == -1
+    assert conv(ctypes.c_void_p(4096), act=2) == -1
+    buf = ctypes.create_string_buffer(256)
+    libdavi.davi_last_error(buf, 256)
+    assert b"davi_conv2d_fwd_pre" in buf.value or b"act" in buf.value
+    assert libdavi.davi_conv2d_wt_batched(a, a, a, a, a, a, a, 1, 1, None) == -1      # transposes go to a second array
+    assert libdavi.davi_conv2d_wt_batched(a, b, a, a, a, a, a, 0, 0, None) == -1
+
+
 def test_ops_refuse_cpu_tensors(libdavi):
     import pytest
     import torch

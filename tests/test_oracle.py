@@ -1,6 +1,7 @@
-"""The oracle checked against closed-form invariants (the reference ships no
-golden vectors: parity unpinned, see oracle/__init__.py) and against an
-independent numpy restatement of the DLM channel map."""
+"""The oracle checked against closed-form invariants and against an independent
+numpy restatement of the DLM channel map.  (The pins proper -- fixtures produced by
+running the reference's own source -- are in tests/test_golden.py, see
+oracle/__init__.py.)"""
 import math
 
 import numpy as np
