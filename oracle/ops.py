@@ -303,3 +303,26 @@ def is_log_likelihood(p_logps, q_logps, nll, num_samples):
 def is_combine_chunks(chunk_lse, num_samples_total):
     """predict_step, vae.py:539: logsumexp over chunks - log K."""
     return torch.logsumexp(torch.stack(chunk_lse, 0), dim=0) - math.log(num_samples_total)
+
+
+# ---------------------------------------------------------------------------
+# 3xTF32 operand split of the convolution / nonlocal kernels (no reference counterpart: the reference convolves in
+# fp32, layers/resnet.py:589-601; this restates what csrc/tc_common.cuh lo_tf32 must produce so that
+# hi*hi' + lo*hi' + hi*lo' recovers the fp32 product)
+# ---------------------------------------------------------------------------
+
+def tf32_split(v):
+    """v (float32 tensor) -> (hi, lo): hi = v truncated to the 10 explicit mantissa bits a TF32 operand keeps (what the
+    tensor core reads of an fp32 bit pattern), lo = (v - hi) rounded to 10 explicit mantissa bits, nearest, ties away
+    from zero (cvt.rna.tf32.f32).  Written with frexp / ldexp arithmetic, not bit masks, so that it is independent of
+    the integer formulation the GPU tests use."""
+    import numpy as np
+    a = v.detach().cpu().numpy().astype(np.float32)
+    m, e = np.frexp(a.astype(np.float64))                      # a = m * 2^e, 0.5 <= |m| < 1
+    hi = np.ldexp(np.trunc(m * 2048.0), e - 11)                # 11 significant bits, toward zero
+    r = a.astype(np.float64) - hi                              # exact: both are fp32 values
+    m, e = np.frexp(r)
+    q = m * 2048.0
+    lo = np.ldexp(np.sign(q) * np.floor(np.abs(q) + 0.5), e - 11)
+    return torch.from_numpy(hi.astype(np.float32)), torch.from_numpy(lo.astype(np.float32))
+

@@ -194,3 +194,28 @@ def test_conv2d_same_restatement_matches_library_conv():
         go = torch.randn_like(y)
         for a, c in zip(torch.autograd.grad(y, (x, w, b), go), torch.autograd.grad(yl, (x, w, b), go)):
             assert torch.allclose(a, c, atol=1e-12)
+
+
+def test_tf32_split_restatement_and_the_gpu_tests_integer_helper_agree():
+    """oracle.ops.tf32_split (frexp / ldexp arithmetic) against the bit-mask helper the GPU tests hold davi_tf32_lo to
+    (tests/test_gpu_kernels._tf32_lo_restatement): identical lo parts, including exact values, rounding ties (away
+    from zero) and both signs; hi + lo reproduces v to 2^-21 relative, lo has at most 11 significant bits."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "gpu_kernel_tests", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_gpu_kernels.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(3)
+    v = torch.cat([torch.randn(4096, generator=g), torch.randn(4096, generator=g) * 1e-3, torch.randn(4096, generator=g) * 300,
+                   torch.tensor([0.0, 1.0, -1.0, 2.0 ** -20, 1.0 + 2.0 ** -12, 1.0 + 2.0 ** -12 + 2.0 ** -23,
+                                 -(1.0 + 2.0 ** -12 + 2.0 ** -23), 1.0 + 2.0 ** -11 + 2.0 ** -12, 3.0 - 2.0 ** -22])]).float()
+    hi, lo = ref.tf32_split(v)
+    assert torch.equal(lo, mod._tf32_lo_restatement(v))
+    assert torch.equal(hi, (v.view(torch.int32) & -8192).view(torch.float32))
+    assert bool(((lo.view(torch.int32) & 8191) == 0).all())
+    err = (hi.double() + lo.double() - v.double()).abs()
+    assert bool((err <= v.double().abs() * 2.0 ** -21).all())
+    i = int((v == 1.0 + 2.0 ** -12 + 2.0 ** -23).nonzero()[0])            # a tie: 2^-12 (1 + 2^-11) -> away from zero
+    assert lo[i].item() == 2.0 ** -12 * (1 + 2.0 ** -10) and lo[i + 1].item() == -lo[i].item()
+
