@@ -86,6 +86,19 @@ def _register_gradients():
         dw = _mod.davi_conv2d_filter_grad(x=x, dy=dy, kh=int(w.shape[1]), kw=int(w.shape[2]))
         return dx, dw, tf.reduce_sum(dy, axis=[0, 1, 2])
 
+    @tf_ops.RegisterGradient("DaviConv2dPre")
+    def _conv2d_pre_grad(op, dy):
+        # kernel_lo is a function of the kernel (DaviTf32Lo) that carries no gradient of its own: the filter gradient is
+        # the one of the plain convolution.  (swish_input: the caller multiplies dx by swish'(x), like ops._ConvTC.)
+        x, w, _w_lo, _b = op.inputs
+        dx = _mod.davi_conv2d_input_grad(dy=dy, kernel_ohwi=w)
+        if op.get_attr("swish_input"):
+            sig = tf.sigmoid(x)
+            dx = dx * (sig * (1.0 + x * (1.0 - sig)))
+            x = x * sig
+        dw = _mod.davi_conv2d_filter_grad(x=x, dy=dy, kh=int(w.shape[1]), kw=int(w.shape[2]))
+        return dx, dw, None, tf.reduce_sum(dy, axis=[0, 1, 2])
+
     @tf_ops.RegisterGradient("DaviLnGeluRes")
     def _ln_gelu_res_grad(op, dy):
         x, gamma, beta, base, res_gamma = op.inputs

@@ -578,6 +578,67 @@ class DaviConv2dOp : public OpKernel {
 };
 REGISTER_KERNEL_BUILDER(Name("DaviConv2d").Device(tf::DEVICE_GPU), DaviConv2dOp);
 
+// DaviTf32Lo / DaviConv2dPre: kernels that live across many calls (once per optimiser step under WeightNorm) carry the lo
+// half of their 3xTF32 split with them: kernel_lo = DaviTf32Lo(kernel_ohwi) once per step, then every DaviConv2dPre of
+// the step loads it by TMA instead of deriving it from each staged weight tile (same bits out).
+REGISTER_OP("DaviTf32Lo")
+    .Input("x: float")
+    .Output("lo: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->input(0));
+      return tf::Status::OK();
+    });
+
+class DaviTf32LoOp : public OpKernel {
+ public:
+  explicit DaviTf32LoOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& x = ctx->input(0);
+    Tensor* lo;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x.shape(), &lo));
+    OP_REQUIRES_OK(ctx, Check(davi_tf32_lo(P(x), P(lo), (int64_t)x.NumElements(), StreamOf(ctx)), "davi_tf32_lo"));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("DaviTf32Lo").Device(tf::DEVICE_GPU), DaviTf32LoOp);
+
+REGISTER_OP("DaviConv2dPre")
+    .Input("x: float").Input("kernel_ohwi: float").Input("kernel_lo: float").Input("bias: float")
+    .Attr("swish_input: bool = false")
+    .Output("y: float")
+    .SetShapeFn([](tf::shape_inference::InferenceContext* c) {
+      c->set_output(0, c->UnknownShape());
+      return tf::Status::OK();
+    });
+
+class DaviConv2dPreOp : public OpKernel {
+ public:
+  explicit DaviConv2dPreOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("swish_input", &swish_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& x = ctx->input(0);
+    const Tensor& w = ctx->input(1);
+    const Tensor& wl = ctx->input(2);
+    const Tensor& b = ctx->input(3);
+    OP_REQUIRES(ctx, x.dims() == 4 && w.dims() == 4 && w.dim_size(3) == x.dim_size(3) && wl.dims() == 4 &&
+                         wl.NumElements() == w.NumElements() && wl.dim_size(0) == w.dim_size(0) && wl.dim_size(3) == w.dim_size(3),
+                tf::errors::InvalidArgument("DaviConv2dPre: x [B,H,W,Cin], kernel and kernel_lo [Cout,kh,kw,Cin]"));
+    const int B = x.dim_size(0), H = x.dim_size(1), W = x.dim_size(2), Cin = x.dim_size(3);
+    const int Cout = w.dim_size(0), kh = w.dim_size(1), kw = w.dim_size(2);
+    Tensor* y;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B, H, W, Cout}), &y));
+    void* ws; size_t wsb;
+    OP_REQUIRES_OK(ctx, ws_.Get(ctx, &ws, &wsb));
+    OP_REQUIRES_OK(ctx, Check(davi_conv2d_fwd_pre(P(x), P(w), P(wl), b.NumElements() ? P(b) : nullptr, P(y), B, H, W, Cin,
+                                                  Cout, kh, kw, Cin, Cout, swish_ ? 1 : 0, ws, wsb, StreamOf(ctx)),
+                              "davi_conv2d_fwd_pre"));
+  }
+ private:
+  ConvWorkspace ws_;
+  bool swish_ = false;
+};
+REGISTER_KERNEL_BUILDER(Name("DaviConv2dPre").Device(tf::DEVICE_GPU), DaviConv2dPreOp);
+
 REGISTER_OP("DaviConv2dInputGrad")
     .Input("dy: float").Input("kernel_ohwi: float")
     .Output("dx: float")
