@@ -9,7 +9,9 @@
 // TMEM.  The lo images are computed ON CHIP from the tiles TMA delivered -- the A tile goes to TMEM as hi | lo
 // (tcgen05.st; the MMAs read A from TMEM, which took 100 KB per chunk of operand reads off shared memory), the lo
 // image of B is a shared -> shared pass -- no split tensors in HBM (the cuDNN path needed davi_split_tf32: 24 B
-// written per element) and no tripled contraction axis.
+// written per element) and no tripled contraction axis.  Weights that a caller keeps across many calls can bring their
+// lo image along (davi_tf32_lo once per optimiser step, davi_conv2d_fwd_pre): the TMA producer then loads the lo tile
+// straight into the lo ring slot and the lo warps only do the A pass -- same bits, taken when the ring has three slots.
 //
 // GEMM view.  MODE 0 (forward / input gradient):
 //     D[m = pixel, n = c_out] = sum_{tap, c_in} X[pixel + tap offset, c_in] * Wt[c_out, tap, c_in]
